@@ -1,0 +1,156 @@
+"""Pipeline-level GPU parity: the lego.yml-shaped NeRFPipeline against the golden outputs of the unmodified
+reference (tests/golden/pipeline.npz) and the reference's own known-answer tests
+(/root/reference/tests/test_pipeline.py:16-29,128-151, test_ray_sampler.py:27-99, test_models.py:19-55)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from yanerf import synthetic as syn
+from yanerf.pipelines.utils import EvaluationMode, sample_grid, scatter_rays_to_image
+from yanerf.testing import build_pipeline, load_synth_nets, oracle_spec, pipeline_cfg
+from yanerf.utils.config import ConfigDict
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("tag,n_fine,std,gain", [("fern", 64, 0.0, 1.0), ("lego", 128, 0.2, 3.0)])
+@pytest.mark.parametrize("coalesce", [True, False])
+def test_eval_render_vs_reference_golden(golden, tag, n_fine, std, gain, coalesce):
+    """Full-grid render, chunked (chunk_size_grid = 64*37 -> 9 chunks) and coalesced, vs the reference output."""
+    g = golden("pipeline")
+    B, H, W, n = 2, 16, 20, 48
+    pipe = build_pipeline(H, W, n, n_fine, std, chunk=64 * 37).to(DEV)
+    pipe.coalesce_chunks = coalesce
+    load_synth_nets(pipe, seeds=(21, 22), gain=gain)
+    poses, focal, image = syn.synth_camera(B, seed=5), torch.full((B, 1), 25.0), syn.synth_image(B, H, W, seed=4)
+    with torch.no_grad():
+        ev = pipe(poses=poses.to(DEV), focal_lengths=focal.to(DEV), image_rgb=image.to(DEV),
+                  evaluation_mode=EvaluationMode.EVALUATION)
+    assert ev["rendered_images"].shape == (B, H, W, 3)
+    assert ev["rendered_depths"].shape == (B, H, W, 1) and ev["rendered_alpha_masks"].shape == (B, H, W, 1)
+    err = float((ev["rendered_images"].cpu() - T(g[f"{tag}_eval_rendered_images"])).abs().max())
+    derr = float((ev["rendered_depths"].cpu() - T(g[f"{tag}_eval_rendered_depths"])).abs().max())
+    print(f"{tag} coalesce={coalesce}: rendered rgb max abs err {err:.2e}, depth {derr:.2e}")
+    if gain == 1.0:
+        assert err <= 2e-3, err
+        assert derr <= 2e-2, derr
+        assert abs(float(ev["loss_rgb_mse"].mean().cpu()) - float(g[f"{tag}_eval_loss_rgb_mse"].mean())) <= 1e-3
+    else:  # stress weights (see test_mlp_forward_golden)
+        assert float((ev["rendered_images"].cpu() - T(g[f"{tag}_eval_rendered_images"])).abs().mean()) <= 2e-2
+    torch.testing.assert_close(ev["rendered_alpha_masks"].cpu(), T(g[f"{tag}_eval_rendered_alpha_masks"]), rtol=0, atol=1e-6)
+    assert set(ev) >= {"loss_rgb_huber", "loss_rgb_mse", "loss_prev_stage_rgb_huber", "loss_prev_stage_rgb_mse",
+                       "rendered_images", "rendered_depths", "rendered_alpha_masks", "objective"}
+    assert ev["objective"].shape == (B,)
+
+
+def test_chunked_equals_coalesced_bitwise():
+    B, H, W = 1, 24, 20
+    pipe = build_pipeline(H, W, 32, 128, 0.0, chunk=64 * 50).to(DEV)
+    load_synth_nets(pipe, seeds=(3, 4), gain=1.0)
+    poses, focal = syn.synth_camera(B, seed=1).to(DEV), torch.full((B, 1), 30.0, device=DEV)
+    outs = []
+    for c in (True, False):
+        pipe.coalesce_chunks = c
+        with torch.no_grad():
+            outs.append(pipe(poses=poses, focal_lengths=focal, evaluation_mode=EvaluationMode.EVALUATION))
+    for k in ("rendered_images", "rendered_depths", "rendered_alpha_masks"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert "loss_rgb_mse" not in outs[0]  # no image_rgb -> no losses (nerf_pipeline.py:249-282)
+
+
+def test_zero_outputer_known_answer():
+    """Reference tests/test_pipeline.py:128-151: zero density -> objective == 0 and render == background,
+    with chunk_size_grid = 30 forcing the chunk loop, custom image size and background_density_bias 0."""
+    from yanerf.pipelines import PIPELINES
+
+    B, H, W = 2, 6, 10
+    cfg = pipeline_cfg(H, W, 8, 16, 0.0, chunk=30)
+    cfg.model = dict(type="ZeroOutputer")
+    cfg.renderer.background_density_bias = 0.0
+    cfg.renderer.bg_color = [0.0]
+    pipe = PIPELINES.build(cfg).to(DEV)
+    pipe.coalesce_chunks = False
+    bg = syn.synth_image(B, H, W, seed=9).to(DEV)
+    poses, focal = syn.synth_camera(B, seed=2).to(DEV), torch.full((B, 1), 12.0, device=DEV)
+    for mode in (EvaluationMode.EVALUATION, EvaluationMode.TRAINING):
+        preds = pipe(poses=poses, focal_lengths=focal, image_rgb=bg, bg_image_rgb=bg, evaluation_mode=mode)
+        assert torch.equal(preds["objective"], torch.zeros(B, device=DEV))
+        if mode == EvaluationMode.EVALUATION:
+            assert torch.equal(preds["rendered_images"], bg)
+    # custom image size at call time
+    bg2 = syn.synth_image(B, 5, 7, seed=10).to(DEV)
+    preds = pipe(poses=poses, focal_lengths=focal, image_rgb=bg2, bg_image_rgb=bg2, image_height=5, image_width=7,
+                 evaluation_mode=EvaluationMode.EVALUATION)
+    assert torch.equal(preds["rendered_images"], bg2)
+
+
+def test_ray_sampler_shapes_and_ranges():
+    """Reference tests/test_ray_sampler.py:27-99."""
+    from yanerf.pipelines.ray_samplers import RAY_SAMPLERS
+
+    B, H, W = 3, 12, 9
+    rs = RAY_SAMPLERS.build(dict(type="RaySampler", image_width=W, image_height=H, n_pts_per_ray_training=6,
+                                 n_pts_per_ray_evaluation=5, n_rays_per_image_sampled_from_mask=11, min_depth=1.0,
+                                 max_depth=4.0))
+    poses, focal = syn.synth_camera(B, seed=3).to(DEV), torch.full((B,), 10.0, device=DEV)
+    tr = rs(poses, focal, EvaluationMode.TRAINING)
+    assert tr.origins.shape == (B, 11, 1, 3) and tr.directions.shape == (B, 11, 1, 3)
+    assert tr.lengths.shape == (B, 11, 1, 6) and tr.xys.shape == (B, 11, 1, 2)
+    assert float(tr.lengths.min()) >= 1.0 and float(tr.lengths.max()) <= 4.0
+    ev = rs(poses, focal, EvaluationMode.EVALUATION, min_depth=0.5, max_depth=2.0)
+    assert ev.lengths.shape == (B, H, W, 5) and ev.xys.shape == (B, H, W, 2)
+    assert float(ev.lengths.min()) >= 0.5 and float(ev.lengths.max()) <= 2.0
+    ev2 = rs(poses, focal, EvaluationMode.EVALUATION, image_height=4, image_width=6)
+    assert ev2.xys.shape == (B, 4, 6, 2)
+    # xys -> flat index identity
+    img = torch.rand(B, H, W, 3, device=DEV)
+    assert torch.equal(sample_grid(img, ev.xys), img)
+    got = sample_grid(img, tr.xys)
+    assert torch.equal(sample_grid(scatter_rays_to_image(got, tr.xys, H, W), tr.xys), got)
+    # per-layer sampling masks
+    masks = torch.rand(B, 2, H, W, device=DEV)
+    tr2 = rs(poses, focal, EvaluationMode.TRAINING, sampling_prob_mask=masks, n_rays_per_image=[4, 3])
+    assert tr2.xys.shape == (B, 7, 1, 2)
+    with pytest.raises(ValueError):
+        rs(poses, focal, EvaluationMode.TRAINING, sampling_prob_mask=masks, n_rays_per_image=[4])
+
+
+def test_model_output_shapes():
+    """Reference tests/test_models.py:19-55 (the latent_dim variant is outside the kernel family and raises)."""
+    from yanerf.pipelines.models import MODELS
+    from yanerf.testing import LEGO_MLP
+
+    mlp = MODELS.build(dict(LEGO_MLP)).to(DEV)
+    o, d, z = torch.rand(2, 4, 5, 3, device=DEV), torch.rand(2, 4, 5, 3, device=DEV), torch.rand(2, 4, 5, 6, device=DEV)
+    out = mlp(o, d, z)
+    assert out["rays_densities"].shape == (2, 4, 5, 6, 1) and out["rays_features"].shape == (2, 4, 5, 6, 3)
+    assert out["aux"] == {}
+    with pytest.raises(ValueError):
+        mlp(o, d, z, global_codes=torch.zeros(2, 1, 2, device=DEV))
+
+
+def test_renderer_two_pass_same_model_runs():
+    """Reference tests/test_renderer.py:17-57: same model object for both passes, per-ray bg colour."""
+    from yanerf.pipelines.models import MODELS
+    from yanerf.pipelines.renderers import RENDERERS
+    from yanerf.pipelines.utils import PartialFunctionWrapper
+    from yanerf.testing import LEGO_MLP
+
+    mlp = PartialFunctionWrapper(MODELS.build(dict(LEGO_MLP))).to(DEV)
+    ren = RENDERERS.build(dict(type="MultipassEmissionAbsorpsionRenderer", n_pts_per_ray_fine_training=4,
+                               n_pts_per_ray_fine_evaluation=8, bg_color=[0.0, 0.0, 0.0]))
+    o, d = torch.rand(3, 4, 5, 3, device=DEV), torch.rand(3, 4, 5, 3, device=DEV)
+    z = torch.sort(torch.rand(3, 4, 5, 6, device=DEV) + 1.0, dim=-1)[0]
+    xy, bg = torch.zeros(3, 4, 5, 2, device=DEV), torch.rand(3, 4, 5, 3, device=DEV)
+    for mode, n in ((EvaluationMode.TRAINING, 10), (EvaluationMode.EVALUATION, 14)):
+        out = ren(o, d, z, xy, bg, implicit_functions=[mlp, mlp], evaluation_mode=mode)
+        assert out.features.shape == (3, 4, 5, 3) and out.depths.shape == (3, 4, 5, 1)
+        assert out.aux["weights"].shape == (3, 4, 5, n) and out.prev_stage.aux["weights"].shape == (3, 4, 5, 6)
+    with pytest.raises(ValueError, match="expects implicit functions"):
+        ren(o, d, z, xy, bg, implicit_functions=[])

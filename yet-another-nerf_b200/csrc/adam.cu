@@ -1,0 +1,42 @@
+// torch.optim.Adam (scripts/run.py:159: lr from the config, betas (0.9, 0.999), eps 1e-8, no weight decay, no
+// amsgrad) as ONE launch over the flat parameter / gradient / moment buffers of both networks.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "mlp_common.cuh"
+
+namespace ynb {
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                   float b1, float b2, float eps, float bc1, float sqrt_bc2,
+                                                   float gscale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * gscale;
+    // exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace ynb
+
+extern "C" int yn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                            float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                            void* stream) {
+  if (n < 0 || step < 1) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_adam_step: n < 0 or step < 1");
+  if (n == 0) return YN_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_adam_step: null pointer");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ynb::adam_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  return ynb::check_launch("yn_adam_step");
+}

@@ -1,0 +1,289 @@
+// Emission-absorption compositing, forward and analytic backward, one warp per ray.
+//
+// Replaces EmissionAbsorptionRaymarcher.forward
+// (yanerf/pipelines/renderers/multipass_emission_absorpsion_renderer.py:154-239): exponential capping,
+// product weights, surface_thickness 1.  The op order of the reference is kept where it matters for
+// rounding: T_i = 1 - (1 - exp(-cumsum_{i-1})), alpha_i = 1 - exp(-x_i), w_i = alpha_i * T_i; the running
+// sum is carried in fp64 and rounded per prefix, which is what torch's CPU cumsum does.
+//
+// Memory-bound: every input element is read once (coalesced 128-byte rows per warp-load), `weights` and the
+// three per-ray outputs are written once; nothing else touches HBM.
+#include <cuda_runtime.h>
+
+#include "mlp_common.cuh"
+
+namespace ynb {
+
+struct MarchParams {
+  yn_march_cfg cfg;
+  const float* sigma;
+  const float* rgb;
+  const float* z;
+  const float* dirs;
+  const float* noise;
+  const float* bg;
+  float* features;
+  float* depths;
+  float* opacities;
+  float* weights;
+  // backward only
+  const float* d_features;
+  const float* d_depths;
+  const float* d_opacities;
+  const float* d_weights;
+  float* d_sigma;
+  float* d_rgb;
+  int64_t R;
+  int P;
+  int C;
+};
+
+__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct SampleState {
+  float x, E, Eprev, alpha, T, w, sraw, delta;
+};
+
+// one 32-sample chunk of the transmittance scan; `carry` = fp64 running sum, `carry_E` = exp(-cumsum) of the
+// sample just before this chunk
+__device__ __forceinline__ SampleState march_chunk(const MarchParams& p, int64_t base, int i, int lane, float dn,
+                                                   double& carry, float& carry_E) {
+  SampleState s;
+  const bool valid = i < p.P;
+  float zi = 0.f, zn = 0.f, sr = 0.f;
+  if (valid) {
+    zi = __ldg(p.z + base + i);
+    sr = __ldg(p.sigma + base + i);
+    if (p.noise != nullptr && p.cfg.density_noise_std > 0.f) sr = sr + __ldg(p.noise + base + i) * p.cfg.density_noise_std;
+    if (i + 1 < p.P) zn = __ldg(p.z + base + i + 1);
+  }
+  float delta = (i == p.P - 1) ? p.cfg.background_opacity : (zn - zi);
+  delta = delta * dn;
+  const float dens = fmaxf(sr, 0.f) + p.cfg.background_density_bias;
+  s.sraw = sr;
+  s.delta = delta;
+  s.x = valid ? delta * dens : 0.f;
+  const double incl = warp_scan_incl(static_cast<double>(s.x), lane) + carry;
+  s.E = expf(-static_cast<float>(incl));
+  float Eprev = __shfl_up_sync(0xffffffffu, s.E, 1);
+  if (lane == 0) Eprev = carry_E;
+  s.Eprev = Eprev;
+  s.T = (i == 0) ? 1.f : 1.f - (1.f - Eprev);
+  s.alpha = 1.f - expf(-s.x);
+  s.w = valid ? s.alpha * s.T : 0.f;
+  carry = __shfl_sync(0xffffffffu, incl, 31);
+  carry_E = __shfl_sync(0xffffffffu, s.E, 31);
+  return s;
+}
+
+template <int kChunks>
+__global__ void __launch_bounds__(256) composite_fwd_kernel(const MarchParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= p.R) return;
+  const int64_t base = ray * p.P;
+  const int C = p.C;
+  const float dx = __ldg(p.dirs + ray * 3), dy = __ldg(p.dirs + ray * 3 + 1), dz = __ldg(p.dirs + ray * 3 + 2);
+  const float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+  float bgv[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) {
+    const int cc = p.cfg.bg_channels == 1 ? 0 : c;
+    bgv[c] = p.bg ? __ldg(p.bg + ray * p.cfg.bg_channels + cc) : p.cfg.bg_const[cc];
+  }
+  double carry = 0.0;
+  float carry_E = 1.f;
+  float feat[4] = {0.f, 0.f, 0.f, 0.f};
+  float depth = 0.f;
+  const int nchunks = kChunks > 0 ? kChunks : (p.P + 31) / 32;
+#pragma unroll
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int i = ch * 32 + lane;
+    const SampleState s = march_chunk(p, base, i, lane, dn, carry, carry_E);
+    if (i < p.P) {
+      p.weights[base + i] = s.w;
+      depth += s.w * __ldg(p.z + base + i);
+      const bool last_hard = p.cfg.hard_background && i == p.P - 1;
+      for (int c = 0; c < C; ++c) {
+        const float col = last_hard ? bgv[c] : __ldg(p.rgb + (base + i) * C + c);
+        feat[c] += s.w * col;
+      }
+    }
+  }
+  depth = warp_sum(depth);
+  for (int c = 0; c < C; ++c) feat[c] = warp_sum(feat[c]);
+  const float opacity = 1.f - carry_E;
+  if (lane == 0) {
+    p.depths[ray] = depth;
+    p.opacities[ray] = opacity;
+    for (int c = 0; c < C; ++c) {
+      float f = feat[c];
+      if (!p.cfg.hard_background) {
+        const float a = p.cfg.blend_output ? opacity : 1.f;
+        f = a * f + (1.f - opacity) * bgv[c];
+      }
+      p.features[ray * C + c] = f;
+    }
+  }
+}
+
+// Backward: two sweeps over the ray (the second hits L1/L2).  Sweep 1 recomputes the forward and accumulates
+//   G = sum_i g_i alpha_i E_{i-1}  (g_i = dL/dw_i) and the pre-blend features; sweep 2 emits
+//   dL/dx_k = g_k E_{k-1}' exp(-x_k) - sum_{i>k} g_i alpha_i E_{i-1} + G_op E_last
+// (E' is T as the forward rounded it), chained through x = delta * (relu(raw + noise) + bias).
+__global__ void __launch_bounds__(256) composite_bwd_kernel(const MarchParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= p.R) return;
+  const int64_t base = ray * p.P;
+  const int C = p.C;
+  const float dx = __ldg(p.dirs + ray * 3), dy = __ldg(p.dirs + ray * 3 + 1), dz = __ldg(p.dirs + ray * 3 + 2);
+  const float dn = sqrtf(dx * dx + dy * dy + dz * dz);
+  float bgv[4] = {0.f, 0.f, 0.f, 0.f}, df[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) {
+    const int cc = p.cfg.bg_channels == 1 ? 0 : c;
+    bgv[c] = p.bg ? __ldg(p.bg + ray * p.cfg.bg_channels + cc) : p.cfg.bg_const[cc];
+    df[c] = __ldg(p.d_features + ray * C + c);
+  }
+  const float ddepth = p.d_depths ? __ldg(p.d_depths + ray) : 0.f;
+  const float dopac = p.d_opacities ? __ldg(p.d_opacities + ray) : 0.f;
+  const int nchunks = (p.P + 31) / 32;
+  const bool hard = p.cfg.hard_background != 0;
+  const bool blend = p.cfg.blend_output != 0 && !hard;
+
+  // ---- sweep 1: opacity, pre-blend features and G = G0 + a * G1 (g_i is affine in the blend factor a)
+  double carry = 0.0;
+  float carry_E = 1.f;
+  float feat[4] = {0.f, 0.f, 0.f, 0.f};
+  double G0 = 0.0, G1 = 0.0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int i = ch * 32 + lane;
+    const SampleState s = march_chunk(p, base, i, lane, dn, carry, carry_E);
+    if (i < p.P) {
+      const bool last_hard = hard && i == p.P - 1;
+      const float g0 = ddepth * __ldg(p.z + base + i) + (p.d_weights ? __ldg(p.d_weights + base + i) : 0.f);
+      float g1 = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float col = __ldg(p.rgb + (base + i) * C + c);
+        if (blend) feat[c] += s.w * col;
+        g1 += df[c] * (last_hard ? bgv[c] : col);
+      }
+      if (i > 0) {
+        const float k = s.alpha * s.Eprev;
+        G0 += static_cast<double>(g0 * k);
+        G1 += static_cast<double>(g1 * k);
+      }
+    }
+  }
+  const float E_last = carry_E;
+  const float opacity = 1.f - E_last;
+  const float a = blend ? opacity : 1.f;
+  float g_op = dopac;
+  if (!hard) {
+    for (int c = 0; c < C; ++c) {
+      const float fc = blend ? warp_sum(feat[c]) : 0.f;
+      g_op += df[c] * (blend ? (fc - bgv[c]) : -bgv[c]);
+    }
+  }
+  double G = G0 + static_cast<double>(a) * G1;
+  G = warp_sum(G);
+  // ---- sweep 2: gradients (prefix in fp64 so that G - prefix stays accurate)
+  double pre = 0.0;
+  carry = 0.0;
+  carry_E = 1.f;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int i = ch * 32 + lane;
+    const SampleState s = march_chunk(p, base, i, lane, dn, carry, carry_E);
+    float g0 = 0.f, g1 = 0.f;
+    const bool last_hard = hard && i == p.P - 1;
+    if (i < p.P) {
+      g0 = ddepth * __ldg(p.z + base + i) + (p.d_weights ? __ldg(p.d_weights + base + i) : 0.f);
+      for (int c = 0; c < C; ++c) g1 += df[c] * (last_hard ? bgv[c] : __ldg(p.rgb + (base + i) * C + c));
+    }
+    const float g = g0 + a * g1;
+    // contribution of sample i to every earlier x_k (through T_i = 1 - (1 - E_{i-1})); none for i = 0 (T = 1).
+    // Same arithmetic as G in sweep 1, so G - prefix cancels to fp64 rounding.
+    const float kk = s.alpha * s.Eprev;
+    const double contrib =
+        (i < p.P && i > 0) ? static_cast<double>(g0 * kk) + static_cast<double>(a) * static_cast<double>(g1 * kk) : 0.0;
+    const double incl = warp_scan_incl(contrib, lane) + pre;
+    pre = __shfl_sync(0xffffffffu, incl, 31);
+    if (i < p.P) {
+      // nothing follows the last sample: exact zero (its delta is 1e10, any residue would be amplified)
+      const float suffix = i == p.P - 1 ? 0.f : static_cast<float>(G - incl);
+      const float dLdx = g * s.T * expf(-s.x) - suffix + g_op * E_last;
+      const float dsig = dLdx * s.delta;
+      p.d_sigma[base + i] = s.sraw > 0.f ? dsig : 0.f;
+      for (int c = 0; c < C; ++c) p.d_rgb[(base + i) * C + c] = last_hard ? 0.f : a * df[c] * s.w;
+    }
+  }
+}
+
+static int validate(const char* name, const yn_march_cfg* cfg, int64_t R, int P, int C) {
+  if (!cfg) return fail(YN_ERR_INVALID_ARGUMENT, "%s: null config", name);
+  if (R < 0 || P < 1 || C < 1 || C > 4) return fail(YN_ERR_INVALID_ARGUMENT, "%s: bad sizes R=%lld P=%d C=%d", name, (long long)R, P, C);
+  if (cfg->bg_channels != 1 && cfg->bg_channels != C)
+    return fail(YN_ERR_INVALID_ARGUMENT, "Wrong number of background color channels.");
+  return YN_OK;
+}
+
+}  // namespace ynb
+
+extern "C" int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_density, const float* rgb,
+                                const float* lengths, const float* directions, const float* noise, const float* bg,
+                                float* features, float* depths, float* opacities, float* weights, int64_t R, int P,
+                                int C, void* stream) {
+  if (int rc = ynb::validate("yn_composite_fwd", cfg, R, P, C)) return rc;
+  if (R == 0) return YN_OK;
+  if (!raw_density || !rgb || !lengths || !directions || !features || !depths || !opacities || !weights)
+    return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_composite_fwd: null pointer");
+  ynb::MarchParams p = {};
+  p.cfg = *cfg;
+  p.sigma = raw_density; p.rgb = rgb; p.z = lengths; p.dirs = directions; p.noise = noise; p.bg = bg;
+  p.features = features; p.depths = depths; p.opacities = opacities; p.weights = weights;
+  p.R = R; p.P = P; p.C = C;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((R + wpb - 1) / wpb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (P == 64) ynb::composite_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(p);
+  else if (P == 128) ynb::composite_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(p);
+  else if (P == 192) ynb::composite_fwd_kernel<6><<<grid, wpb * 32, 0, st>>>(p);
+  else ynb::composite_fwd_kernel<0><<<grid, wpb * 32, 0, st>>>(p);
+  return ynb::check_launch("yn_composite_fwd");
+}
+
+extern "C" int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_density, const float* rgb,
+                                const float* lengths, const float* directions, const float* noise, const float* bg,
+                                const float* d_features, const float* d_depths, const float* d_opacities,
+                                const float* d_weights, float* d_raw_density, float* d_rgb, int64_t R, int P, int C,
+                                void* stream) {
+  if (int rc = ynb::validate("yn_composite_bwd", cfg, R, P, C)) return rc;
+  if (R == 0) return YN_OK;
+  if (!raw_density || !rgb || !lengths || !directions || !d_features || !d_raw_density || !d_rgb)
+    return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_composite_bwd: null pointer");
+  ynb::MarchParams p = {};
+  p.cfg = *cfg;
+  p.sigma = raw_density; p.rgb = rgb; p.z = lengths; p.dirs = directions; p.noise = noise; p.bg = bg;
+  p.d_features = d_features; p.d_depths = d_depths; p.d_opacities = d_opacities; p.d_weights = d_weights;
+  p.d_sigma = d_raw_density; p.d_rgb = d_rgb;
+  p.R = R; p.P = P; p.C = C;
+  const int wpb = 8;
+  ynb::composite_bwd_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return ynb::check_launch("yn_composite_bwd");
+}

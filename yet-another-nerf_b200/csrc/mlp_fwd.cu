@@ -1,0 +1,398 @@
+// Fused NeRF-MLP forward for sm_100a.
+//
+// Replaces NeRFMLP.forward (yanerf/pipelines/models/nerf_mlp.py:117-177) together with
+// ray_bundle_to_ray_points and HarmonicEmbedding.forward (models/utils.py:90-103,214-245):
+// points = o + z*d, 63-channel harmonic embedding, the 8x256 skip trunk, density head, intermediate
+// linear, LinearWithRepeat colour hidden layer and the sigmoid colour head, in ONE persistent kernel.
+//
+// One CTA per SM, 320 threads:
+//   warp 0      TMA producer: streams 16 KB weight blocks [128 n x 64 k] (pre-swizzled image) through a
+//               4-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx.
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128, K=16, fp32 accumulate in
+//               TMEM); A = activation tile in shared memory (K-major, 128B swizzle), B = ring slot.
+//   warps 2-5   epilogue group 0, warps 6-9 epilogue group 1: tcgen05.ld the accumulator, add bias, ReLU,
+//               convert to 16 bit and write the next layer's A operand back to shared memory.  The first
+//               "epilogue" of a tile computes the embedding, the last ones compute the fp32 heads.
+// Two 128-point tiles are in flight per CTA (TMEM columns [0,256) and [256,512)); the MMA warp alternates
+// between them layer by layer so the epilogue of one tile overlaps the MMAs of the other.
+#include <cuda_runtime.h>
+
+#include "mlp_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ynb {
+
+constexpr int kRing = 4;
+constexpr int kFwdThreads = 320;
+constexpr int kSmemAct = 0;                              // [2][4][16 KB]
+constexpr int kSmemEmb = kSmemAct + 2 * 4 * kBlkBytes;   // [2][16 KB]
+constexpr int kSmemRing = kSmemEmb + 2 * kBlkBytes;      // [4][16 KB]
+constexpr int kSmemBar = kSmemRing + kRing * kBlkBytes;  // barriers
+constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kFwdSmemBytes = kSmemTotal + 1024;         // + alignment slack
+
+struct FwdParams {
+  Arch arch;
+  const float* origins;
+  const float* directions;
+  const float* lengths;
+  const float* dirbias;  // [R][128]
+  const uint8_t* wpack;
+  const float* aux;
+  float* density;
+  float* rgb;
+  uint8_t* stash;  // nullptr in inference
+  int64_t n_points;
+  int P;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int kFmt>
+__device__ __forceinline__ uint16_t to_half_bits(float x) {
+  if (kFmt == 1) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    return *reinterpret_cast<uint16_t*>(&h);
+  } else {
+    __half h = __float2half_rn(x);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+template <int kFmt, bool kStash>
+__global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_act = smem_base + kSmemAct;
+  const uint32_t s_emb = smem_base + kSmemEmb;
+  const uint32_t s_ring = smem_base + kSmemRing;
+  const uint32_t s_bar = smem_base + kSmemBar;
+  // barrier layout (8 B each): full[4], empty[4], tmem_full[2], act_ready[2], then tmem ptr
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kRing, bar_tfull = s_bar + 16 * kRing,
+                 bar_ready = bar_tfull + 16, s_tmem_ptr = bar_ready + 16;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const Arch& A = p.arch;
+  const int L = A.n_mma_layers();
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar_tfull + 8 * g, 1);
+      mbar_init(bar_ready + 8 * g, 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s_tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        int soff = 0;
+        for (int l = 0; l < L; ++l) {
+          const int nst = A.stages(l);
+          const uint8_t* src = p.wpack + (size_t)soff * kBlkBytes;
+          for (int g = 0; g < 2; ++g) {
+            for (int s = 0; s < nst; ++s) {
+              mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+              mbar_arrive_expect_tx(bar_full + 8 * slot, kBlkBytes);
+              bulk_g2s(s_ring + slot * kBlkBytes, src + (size_t)s * kBlkBytes, kBlkBytes, bar_full + 8 * slot);
+              if (++slot == kRing) { slot = 0; phase ^= 1; }
+            }
+          }
+          soff += nst;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(128, 128, kFmt, 0, 0);
+      uint32_t slot = 0, phase = 0;
+      uint32_t ready_phase[2] = {0, 0};
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          const int nkbh = A.nkb_hidden(l);
+          const int nkb = A.nkb(l);
+          const int nnh = A.nnh(l);
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(bar_ready + 8 * g, ready_phase[g]);
+            ready_phase[g] ^= 1;
+            tc_fence_after();
+            for (int nh = 0; nh < nnh; ++nh) {
+              const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
+              for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(bar_full + 8 * slot, phase);
+                tc_fence_after();
+                const uint32_t a_base = (kb < nkbh) ? (s_act + (g * 4 + kb) * kBlkBytes) : (s_emb + g * kBlkBytes);
+                const uint32_t b_base = s_ring + slot * kBlkBytes;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16(d_tmem, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
+                           (kb | k) != 0);
+                }
+                umma_commit(bar_empty + 8 * slot);
+                if (++slot == kRing) { slot = 0; phase ^= 1; }
+              }
+            }
+            umma_commit(bar_tfull + 8 * g);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue groups
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
+    const uint32_t act_g = s_act + g * 4 * kBlkBytes;
+    const uint32_t emb_g = s_emb + g * kBlkBytes;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const bool stash_leader = (warp - 2) % 4 == 0 && lane == 0;
+    const int nfx = A.n_freq_xyz;
+    const int blocks_per_tile = A.stash_blocks_per_tile();
+    uint32_t tf_phase = 0;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + g;
+      const int64_t gidx = tile * kTileM + row;
+      const bool valid = gidx < p.n_points;
+      const int64_t ray = valid ? gidx / p.P : 0;
+      uint8_t* stash_tile = kStash ? p.stash + (size_t)tile * blocks_per_tile * kBlkBytes : nullptr;
+      const bool tile_live = tile < n_tiles;
+
+      if (kStash) {
+        if (stash_leader) bulk_wait_read<0>();
+        named_bar_sync(1 + g, 128);
+      }
+      // ---- embedding (models/utils.py:90-103): [sin(x f_k) | cos(x f_k) | x], channel a*L+k
+      {
+        float pt[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const float z = __ldg(p.lengths + gidx);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            pt[a] = __fadd_rn(__ldg(p.origins + ray * 3 + a), __fmul_rn(z, __ldg(p.directions + ray * 3 + a)));
+        }
+        for (int a = 0; a < 3; ++a) {
+          float f = 1.f;
+          for (int k = 0; k < nfx; ++k, f *= 2.f) {
+            float s, c;
+            sincosf(pt[a] * f, &s, &c);
+            if (!valid) { s = 0.f; c = 0.f; }
+            const int ch = a * nfx + k;
+            st_shared_u16(emb_g + sw128_offset(row, ch), to_half_bits<kFmt>(s));
+            st_shared_u16(emb_g + sw128_offset(row, 3 * nfx + ch), to_half_bits<kFmt>(c));
+          }
+          st_shared_u16(emb_g + sw128_offset(row, 6 * nfx + a), to_half_bits<kFmt>(pt[a]));
+        }
+        for (int ch = 6 * nfx + 3; ch < 64; ++ch) st_shared_u16(emb_g + sw128_offset(row, ch), 0);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_ready + 8 * g);
+      if (kStash) {
+        named_bar_sync(1 + g, 128);
+        if (stash_leader && tile_live) {
+          bulk_s2g(stash_tile, emb_g, kBlkBytes);
+          bulk_commit();
+        }
+      }
+
+      float dens = 0.f;
+      for (int l = 0; l < L; ++l) {
+        mbar_wait(bar_tfull + 8 * g, tf_phase);
+        tf_phase ^= 1;
+        tc_fence_after();
+        const bool is_color = (l == L - 1);
+        const bool is_inter = (l == L - 2);
+        const bool is_last_trunk = (l == L - 3);
+        const bool writes_act = !is_color || kStash;
+        if (kStash) {
+          // the previous layer's stash store may still be reading this tile's activation buffer
+          if (stash_leader) bulk_wait_read<0>();
+          named_bar_sync(1 + g, 128);
+        }
+        if (!is_color) {
+          const float* bias = p.aux + A.aux_bias(l);
+          const float* wd = p.aux + A.aux_wd();
+#pragma unroll 1
+          for (int cb = 0; cb < 8; cb += 2) {
+            uint32_t v[2][32];
+            tmem_ld32(t_row + cb * 32, v[0]);
+            tmem_ld32(t_row + cb * 32 + 32, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = (cb + h) * 32;
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+                float x0 = __uint_as_float(v[h][j]) + b.x, x1 = __uint_as_float(v[h][j + 1]) + b.y;
+                float x2 = __uint_as_float(v[h][j + 2]) + b.z, x3 = __uint_as_float(v[h][j + 3]) + b.w;
+                if (!is_inter) {
+                  x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+                }
+                if (is_last_trunk) {
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
+                  dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
+                  dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
+                }
+                pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
+                pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
+              }
+              const uint32_t blk = act_g + ((cb + h) >> 1) * kBlkBytes + row_off;
+              const uint32_t u0 = ((cb + h) & 1) * 4;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
+          }
+          if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
+        } else {
+          // colour hidden layer: + per-ray direction bias (LinearWithRepeat), ReLU, then the colour head
+          const float* db = p.dirbias + ray * kDirPad;
+          const float* w2 = p.aux + A.aux_w2();
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int cb = 0; cb < 4; cb += 2) {
+            uint32_t v[2][32];
+            tmem_ld32(t_row + cb * 32, v[0]);
+            tmem_ld32(t_row + cb * 32 + 32, v[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = (cb + h) * 32;
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(db + c0 + j));
+                const float x0 = fmaxf(__uint_as_float(v[h][j]) + b.x, 0.f);
+                const float x1 = fmaxf(__uint_as_float(v[h][j + 1]) + b.y, 0.f);
+                const float x2 = fmaxf(__uint_as_float(v[h][j + 2]) + b.z, 0.f);
+                const float x3 = fmaxf(__uint_as_float(v[h][j + 3]) + b.w, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0 + j));
+                  acc[c] = fmaf(x0, w.x, acc[c]); acc[c] = fmaf(x1, w.y, acc[c]);
+                  acc[c] = fmaf(x2, w.z, acc[c]); acc[c] = fmaf(x3, w.w, acc[c]);
+                }
+                if (kStash) {
+                  pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
+                  pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
+                }
+              }
+              if (kStash) {
+                const uint32_t blk = act_g + ((cb + h) >> 1) * kBlkBytes + row_off;
+                const uint32_t u0 = ((cb + h) & 1) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              }
+            }
+          }
+          if (valid) {
+            const int C = A.color_dim;
+            for (int c = 0; c < C; ++c) {
+              const float x = acc[c] + __ldg(p.aux + A.aux_b2() + c);
+              p.rgb[gidx * C + c] = 1.f / (1.f + expf(-x));
+            }
+          }
+        }
+        tc_fence_before();
+        if (writes_act) fence_proxy_async_smem();
+        if (!is_color) mbar_arrive(bar_ready + 8 * g);
+        if (kStash) {
+          named_bar_sync(1 + g, 128);
+          if (stash_leader && tile_live) {
+            uint8_t* dst = stash_tile + (size_t)A.stash_block_of_layer(l) * kBlkBytes;
+            const int nblk = is_color ? 2 : 4;
+            for (int b = 0; b < nblk; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, act_g + b * kBlkBytes, kBlkBytes);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (kStash && stash_leader) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int launch_fwd(const FwdParams& p, cudaStream_t stream) {
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+  if (grid == 0) return YN_OK;
+  auto run = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+    kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
+  };
+  const bool st = p.stash != nullptr;
+  if (p.arch.fmt == 1) {
+    if (st) run(mlp_fwd_kernel<1, true>); else run(mlp_fwd_kernel<1, false>);
+  } else {
+    if (st) run(mlp_fwd_kernel<0, true>); else run(mlp_fwd_kernel<0, false>);
+  }
+  return check_launch("yn_mlp_fwd");
+}
+
+}  // namespace ynb
+
+extern "C" int yn_mlp_fwd(const yn_mlp_arch* arch, const float* origins, const float* directions,
+                          const float* lengths, const float* dirbias, const void* wpack, const float* aux,
+                          float* density, float* rgb, void* stash, int64_t R, int P, void* stream) {
+  if (int rc = ynb::check_arch(arch)) return rc;
+  if (R < 0 || P <= 0) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_fwd: bad sizes R=%lld P=%d", (long long)R, P);
+  if (R == 0) return YN_OK;
+  if (!origins || !directions || !lengths || !dirbias || !wpack || !aux || !density || !rgb)
+    return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_fwd: null pointer");
+  ynb::FwdParams p;
+  p.arch = ynb::arch_from_c(arch);
+  p.origins = origins;
+  p.directions = directions;
+  p.lengths = lengths;
+  p.dirbias = dirbias;
+  p.wpack = static_cast<const uint8_t*>(wpack);
+  p.aux = aux;
+  p.density = density;
+  p.rgb = rgb;
+  p.stash = static_cast<uint8_t*>(stash);
+  p.n_points = R * P;
+  p.P = P;
+  return ynb::launch_fwd(p, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,199 @@
+// Weight preparation for the fused NeRF-MLP kernels:
+//   yn_mlp_pack_weights  fp32 master parameters (state-dict order, nerf_mlp.py:61-83) -> 16-bit tensor-core
+//                        blocks [128 x 64] in the 128-byte-swizzled shared-memory image the UMMA descriptors
+//                        expect, in the exact order the kernels stream them, plus a small fp32 "aux" buffer
+//                        (padded biases, density head, colour head).
+//   yn_mlp_dirbias       the per-ray half of LinearWithRepeat (models/utils.py:207-211) on the harmonic
+//                        embedding of the normalised directions (nerf_mlp.py:97-115).
+#include <cuda_runtime.h>
+
+#include "mlp_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ynb {
+
+template <int kFmt>
+__global__ void pack_weights_kernel(const Arch A, const float* __restrict__ params, uint8_t* __restrict__ wpack,
+                                    int n_units) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_units) return;
+  const int s = idx >> 10;  // 1024 16-byte units per block
+  const int unit = idx & 1023;
+  const int r = unit >> 3, u = unit & 7;
+  const int L = A.n_mma_layers();
+  const int fwd_total = A.total_stages();
+  float vals[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) vals[i] = 0.f;
+
+  if (s < fwd_total) {
+    // forward block (l, nh, kb): rows = output features nh*128 + r, cols = input columns of K-block kb
+    int l = 0, off = 0;
+    while (l < L && s >= off + A.stages(l)) { off += A.stages(l); ++l; }
+    const int local = s - off;
+    const int nkb = A.nkb(l);
+    const int nh = local / nkb, kb = local % nkb;
+    const int n = nh * 128 + r;
+    const int din = A.din(l);
+    if (n < A.dout(l)) {
+      const float* W = params + A.w_offset(l);
+      const bool emb_blk = kb >= A.nkb_hidden(l);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = u * 8 + i;
+        int col = -1;
+        if (emb_blk) {
+          if (c < A.embed_xyz()) col = A.hidden_in(l) + c;
+        } else {
+          const int k = kb * 64 + c;
+          if (k < A.hidden_in(l)) col = k;
+        }
+        if (col >= 0) vals[i] = W[(int64_t)n * din + col];
+      }
+    }
+  } else {
+    // data-gradient block of layer l (walked in reverse layer order): rows = input feature nh*128 + r,
+    // cols = output feature kb*64 + c, value W_l[out][in]
+    int l = L - 1, off = fwd_total;
+    while (l > 0 && s >= off + A.bwd_stages(l)) { off += A.bwd_stages(l); --l; }
+    const int local = s - off;
+    const int nkb = A.bwd_stages(l) / 2;
+    const int nh = local / nkb, kb = local % nkb;
+    const int n = nh * 128 + r;
+    const int din = A.din(l);
+    if (n < A.hidden_in(l)) {
+      const float* W = params + A.w_offset(l);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kb * 64 + u * 8 + i;
+        if (k < A.dout(l)) vals[i] = W[(int64_t)k * din + n];
+      }
+    }
+  }
+  uint4 out;
+  out.x = Half2Pack<kFmt>::pack(vals[0], vals[1]);
+  out.y = Half2Pack<kFmt>::pack(vals[2], vals[3]);
+  out.z = Half2Pack<kFmt>::pack(vals[4], vals[5]);
+  out.w = Half2Pack<kFmt>::pack(vals[6], vals[7]);
+  *reinterpret_cast<uint4*>(wpack + (size_t)s * kBlkBytes + r * 128 + ((u ^ (r & 7)) << 4)) = out;
+}
+
+__global__ void pack_aux_kernel(const Arch A, const float* __restrict__ params, float* __restrict__ aux, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = 0.f;
+  if (i < A.aux_wd()) {
+    const int l = i / kInner, c = i % kInner;
+    if (c < A.dout(l)) v = params[A.b_offset(l) + c];
+  } else if (i < A.aux_bd()) {
+    const int c = i - A.aux_wd();
+    if (c < A.hidden_last) v = params[A.density_w_offset() + c];
+  } else if (i < A.aux_w2()) {
+    if (i == A.aux_bd()) v = params[A.density_b_offset()];
+  } else if (i < A.aux_b2()) {
+    const int c = (i - A.aux_w2()) / kDirPad, j = (i - A.aux_w2()) % kDirPad;
+    if (c < A.color_dim && j < A.hidden_dir) v = params[A.color2_w_offset() + (int64_t)c * A.hidden_dir + j];
+  } else {
+    const int c = i - A.aux_b2();
+    if (c < A.color_dim) v = params[A.color2_b_offset() + c];
+  }
+  aux[i] = v;
+}
+
+// one block = 8 rays x 128 outputs
+__global__ void __launch_bounds__(128) dirbias_kernel(const Arch A, const float* __restrict__ params,
+                                                     const float* __restrict__ directions,
+                                                     float* __restrict__ dirbias, int64_t R) {
+  __shared__ float s_emb[8][64];
+  __shared__ float s_w[kDirPad * 64];
+  const int ed = A.embed_dir();
+  const int din = A.din(A.n_layers + 1);
+  const float* W = params + A.w_offset(A.n_layers + 1);
+  const float* bc = params + A.b_offset(A.n_layers + 1);
+  for (int i = threadIdx.x; i < A.hidden_dir * ed; i += blockDim.x) {
+    const int j = i / ed, k = i % ed;
+    s_w[j * 64 + k] = W[(int64_t)j * din + A.hidden_last + k];
+  }
+  const int64_t ray0 = (int64_t)blockIdx.x * 8;
+  if (threadIdx.x < 8) {
+    const int64_t ray = ray0 + threadIdx.x;
+    if (ray < R) {
+      // F.normalize(d, dim=-1) = d / max(|d|, 1e-12)  (nerf_mlp.py:105)
+      const float dx = directions[ray * 3], dy = directions[ray * 3 + 1], dz = directions[ray * 3 + 2];
+      const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+      const float d[3] = {dx / nrm, dy / nrm, dz / nrm};
+      const int nf = A.n_freq_dir;
+      for (int a = 0; a < 3; ++a) {
+        float f = 1.f;
+        for (int k = 0; k < nf; ++k, f *= 2.f) {
+          float s, c;
+          sincosf(d[a] * f, &s, &c);
+          s_emb[threadIdx.x][a * nf + k] = s;
+          s_emb[threadIdx.x][3 * nf + a * nf + k] = c;
+        }
+        s_emb[threadIdx.x][6 * nf + a] = d[a];
+      }
+    }
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  for (int i = 0; i < 8; ++i) {
+    const int64_t ray = ray0 + i;
+    if (ray >= R) break;
+    float acc = 0.f;
+    if (j < A.hidden_dir) {
+      acc = bc[j];
+      for (int k = 0; k < ed; ++k) acc = fmaf(s_w[j * 64 + k], s_emb[i][k], acc);
+    }
+    dirbias[ray * kDirPad + j] = acc;
+  }
+}
+
+}  // namespace ynb
+
+extern "C" int yn_mlp_pack_weights(const yn_mlp_arch* arch, const float* params, void* wpack, float* aux,
+                                   void* stream) {
+  if (int rc = ynb::check_arch(arch)) return rc;
+  if (!params || !wpack || !aux) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_pack_weights: null pointer");
+  const ynb::Arch A = ynb::arch_from_c(arch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_units = A.total_stages_all() * 1024;
+  if (A.fmt == 1)
+    ynb::pack_weights_kernel<1><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, static_cast<uint8_t*>(wpack), n_units);
+  else
+    ynb::pack_weights_kernel<0><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, static_cast<uint8_t*>(wpack), n_units);
+  const int na = A.aux_floats();
+  ynb::pack_aux_kernel<<<(na + 255) / 256, 256, 0, st>>>(A, params, aux, na);
+  return ynb::check_launch("yn_mlp_pack_weights");
+}
+
+extern "C" int yn_mlp_dirbias(const yn_mlp_arch* arch, const float* params, const float* directions,
+                              float* dirbias, int64_t R, void* stream) {
+  if (int rc = ynb::check_arch(arch)) return rc;
+  if (R < 0) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_dirbias: R < 0");
+  if (R == 0) return YN_OK;
+  if (!params || !directions || !dirbias) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_dirbias: null pointer");
+  const ynb::Arch A = ynb::arch_from_c(arch);
+  ynb::dirbias_kernel<<<(unsigned)((R + 7) / 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, params, directions,
+                                                                                         dirbias, R);
+  return ynb::check_launch("yn_mlp_dirbias");
+}
+
+extern "C" int64_t yn_mlp_param_count(const yn_mlp_arch* arch) {
+  if (ynb::check_arch(arch)) return -1;
+  return ynb::arch_from_c(arch).param_count();
+}
+extern "C" int64_t yn_mlp_wpack_bytes(const yn_mlp_arch* arch) {
+  if (ynb::check_arch(arch)) return -1;
+  return (int64_t)ynb::arch_from_c(arch).total_stages_all() * ynb::kBlkBytes;
+}
+extern "C" int64_t yn_mlp_aux_floats(const yn_mlp_arch* arch) {
+  if (ynb::check_arch(arch)) return -1;
+  return ynb::arch_from_c(arch).aux_floats();
+}
+extern "C" int64_t yn_mlp_stash_bytes(const yn_mlp_arch* arch, int64_t n_points) {
+  if (ynb::check_arch(arch) || n_points < 0) return -1;
+  const int64_t n_tiles = (n_points + ynb::kTileM - 1) / ynb::kTileM;
+  // the forward kernel works on tile pairs; keep room for the (masked) odd partner
+  return ((n_tiles + 1) / 2 * 2) * (int64_t)ynb::arch_from_c(arch).stash_blocks_per_tile() * ynb::kBlkBytes;
+}

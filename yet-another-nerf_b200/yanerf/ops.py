@@ -1,0 +1,325 @@
+"""Operator layer: torch-facing wrappers (and autograd Functions) over the C ABI.
+
+Every function takes/returns CUDA fp32 tensors with rays flattened to `[R, ...]`.
+Nothing here computes on the CPU or with torch ops: the arithmetic happens in
+libyanerf_b200.so; torch only owns the memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+
+# --------------------------------------------------------------------------- #
+# ray sampler
+# --------------------------------------------------------------------------- #
+def ray_bundle(
+    poses: torch.Tensor,
+    focal: torch.Tensor,
+    xy: Optional[torch.Tensor],
+    depths: torch.Tensor,
+    u: Optional[torch.Tensor],
+    n_rays: int,
+    width: int,
+    height: int,
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """`_xy_to_ray_bundle` + `_jiggle_within_stratas` (ray_sampler.py:249-314, 361-386).
+
+    poses [B,3,4] (any strides with unit column stride), focal [B], xy [B,n,2] or
+    None for the full `height x width` grid, depths [P], u [B,n,P] or None.
+    Returns origins [B,n,3], directions [B,n,3], lengths [B,n,P], xys [B,n,2].
+    """
+    B = poses.shape[0]
+    P = depths.shape[0]
+    dev = poses.device
+    if poses.dtype != torch.float32 or poses.stride(2) != 1:
+        poses = poses.float().contiguous()
+    focal = N.f32c(focal.reshape(B))
+    full = xy is None
+    if not full:
+        xy = N.f32c(xy)
+    origins = torch.empty(B, n_rays, 3, device=dev)
+    directions = torch.empty(B, n_rays, 3, device=dev)
+    lengths = torch.empty(B, n_rays, P, device=dev)
+    xys = torch.empty(B, n_rays, 2, device=dev) if full else xy
+    N.check(
+        N.lib().yn_ray_bundle(
+            ctypes.c_void_p(poses.data_ptr()), poses.stride(0), poses.stride(1), N.ptr(focal), N.ptr(xy),
+            N.ptr(N.f32c(depths)), N.ptr(None if u is None else N.f32c(u)), N.ptr(origins), N.ptr(directions),
+            N.ptr(lengths), N.ptr(xys if full else None), B, n_rays, P, width, height, 1 if full else 0,
+            N.stream_ptr(),
+        )
+    )
+    return origins, directions, lengths, xys
+
+
+# --------------------------------------------------------------------------- #
+# NeRF MLP
+# --------------------------------------------------------------------------- #
+@dataclass
+class MlpPlan:
+    """Device-side state of one NeRFMLP: architecture + packed tensor-core weights."""
+
+    arch: N.MlpArch
+    n_params: int
+    wpack: torch.Tensor  # uint8
+    aux: torch.Tensor  # fp32
+
+    @staticmethod
+    def create(arch: N.MlpArch, device) -> "MlpPlan":
+        L = N.lib()
+        n_params = L.yn_mlp_param_count(ctypes.byref(arch))
+        if n_params < 0:
+            raise NotImplementedError(L.yn_last_error_string().decode())
+        wbytes = L.yn_mlp_wpack_bytes(ctypes.byref(arch))
+        naux = L.yn_mlp_aux_floats(ctypes.byref(arch))
+        return MlpPlan(
+            arch=arch,
+            n_params=int(n_params),
+            wpack=torch.empty(int(wbytes), dtype=torch.uint8, device=device),
+            aux=torch.empty(int(naux), dtype=torch.float32, device=device),
+        )
+
+    def pack(self, flat_params: torch.Tensor) -> None:
+        assert flat_params.numel() == self.n_params
+        N.check(
+            N.lib().yn_mlp_pack_weights(
+                ctypes.byref(self.arch), N.ptr(flat_params), N.ptr(self.wpack, torch.uint8), N.ptr(self.aux), N.stream_ptr()
+            )
+        )
+
+
+def mlp_forward_raw(
+    plan: MlpPlan, flat_params: torch.Tensor, origins: torch.Tensor, directions: torch.Tensor, lengths: torch.Tensor,
+    stash: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """origins/directions [R,3], lengths [R,P] -> raw density [R,P], rgb [R,P,C] (plan already packed)."""
+    R, P = lengths.shape
+    dev = lengths.device
+    C = plan.arch.color_dim
+    density = torch.empty(R, P, device=dev)
+    rgb = torch.empty(R, P, C, device=dev)
+    if R == 0:
+        return density, rgb
+    dirbias = torch.empty(R, 128, device=dev)
+    L = N.lib()
+    N.check(L.yn_mlp_dirbias(ctypes.byref(plan.arch), N.ptr(flat_params), N.ptr(directions), N.ptr(dirbias), R, N.stream_ptr()))
+    N.check(
+        L.yn_mlp_fwd(
+            ctypes.byref(plan.arch), N.ptr(origins), N.ptr(directions), N.ptr(lengths), N.ptr(dirbias),
+            N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(density), N.ptr(rgb),
+            N.ptr(stash, torch.uint8), R, P, N.stream_ptr(),
+        )
+    )
+    return density, rgb
+
+
+class MlpFunction(torch.autograd.Function):
+    """autograd node of NeRFMLP.forward: inputs (origins, directions, lengths) carry no gradient
+    (the reference never differentiates w.r.t. the rays); the flat parameter vector does."""
+
+    @staticmethod
+    def forward(ctx, flat_params, origins, directions, lengths, plan: MlpPlan):
+        R, P = lengths.shape
+        need_grad = flat_params.requires_grad and torch.is_grad_enabled()
+        stash = None
+        if need_grad and R > 0:
+            nbytes = N.lib().yn_mlp_stash_bytes(ctypes.byref(plan.arch), R * P)
+            stash = torch.empty(int(nbytes), dtype=torch.uint8, device=lengths.device)
+        density, rgb = mlp_forward_raw(plan, flat_params, origins, directions, lengths, stash)
+        ctx.plan = plan
+        ctx.stash = stash
+        ctx.save_for_backward(flat_params, directions, rgb)
+        ctx.shape = (R, P)
+        return density, rgb
+
+    @staticmethod
+    def backward(ctx, d_density, d_rgb):
+        flat_params, directions, rgb = ctx.saved_tensors
+        plan: MlpPlan = ctx.plan
+        R, P = ctx.shape
+        grads = torch.zeros_like(flat_params)
+        if R > 0:
+            L = N.lib()
+            d_density = N.f32c(d_density) if d_density is not None else torch.zeros(R, P, device=rgb.device)
+            d_rgb = N.f32c(d_rgb) if d_rgb is not None else torch.zeros_like(rgb)
+            wbytes = L.yn_mlp_bwd_workspace_bytes(ctypes.byref(plan.arch), R * P)
+            work = torch.empty(int(wbytes), dtype=torch.uint8, device=rgb.device)
+            N.check(
+                L.yn_mlp_bwd(
+                    ctypes.byref(plan.arch), N.ptr(directions), N.ptr(rgb), N.ptr(d_density), N.ptr(d_rgb),
+                    N.ptr(flat_params), N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(ctx.stash, torch.uint8),
+                    N.ptr(work, torch.uint8), N.ptr(grads), R, P, N.stream_ptr(),
+                )
+            )
+        ctx.stash = None
+        return grads, None, None, None, None
+
+
+# --------------------------------------------------------------------------- #
+# emission-absorption compositing
+# --------------------------------------------------------------------------- #
+def march_cfg(background_opacity: float, background_density_bias: float, density_noise_std: float, blend_output: bool,
+              hard_background: bool, bg_const: Sequence[float]) -> N.MarchCfg:
+    cfg = N.MarchCfg()
+    cfg.background_opacity = background_opacity
+    cfg.background_density_bias = background_density_bias
+    cfg.density_noise_std = density_noise_std
+    cfg.blend_output = int(blend_output)
+    cfg.hard_background = int(hard_background)
+    cfg.bg_channels = len(bg_const)
+    for i, v in enumerate(bg_const):
+        cfg.bg_const[i] = float(v)
+    return cfg
+
+
+class CompositeFunction(torch.autograd.Function):
+    """EmissionAbsorptionRaymarcher.forward with its analytic backward."""
+
+    @staticmethod
+    def forward(ctx, raw_density, rgb, lengths, directions, noise, bg, cfg: N.MarchCfg):
+        R, P = lengths.shape
+        C = rgb.shape[-1]
+        dev = lengths.device
+        raw_density, rgb, lengths, directions = (N.f32c(t) for t in (raw_density, rgb, lengths, directions))
+        noise = None if noise is None else N.f32c(noise)
+        bg = None if bg is None else N.f32c(bg)
+        if bg is not None:
+            cfg = _copy_cfg(cfg)
+            cfg.bg_channels = bg.shape[-1]
+        features = torch.empty(R, C, device=dev)
+        depths = torch.empty(R, 1, device=dev)
+        opacities = torch.empty(R, 1, device=dev)
+        weights = torch.empty(R, P, device=dev)
+        N.check(
+            N.lib().yn_composite_fwd(
+                ctypes.byref(cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
+                N.ptr(bg), N.ptr(features), N.ptr(depths), N.ptr(opacities), N.ptr(weights), R, P, C, N.stream_ptr(),
+            )
+        )
+        ctx.cfg = cfg
+        ctx.has = (noise is not None, bg is not None)
+        saved = [raw_density, rgb, lengths, directions] + ([noise] if noise is not None else []) + ([bg] if bg is not None else [])
+        ctx.save_for_backward(*saved)
+        return features, depths, opacities, weights
+
+    @staticmethod
+    def backward(ctx, d_features, d_depths, d_opacities, d_weights):
+        saved = list(ctx.saved_tensors)
+        raw_density, rgb, lengths, directions = saved[:4]
+        rest = saved[4:]
+        noise = rest.pop(0) if ctx.has[0] else None
+        bg = rest.pop(0) if ctx.has[1] else None
+        R, P = lengths.shape
+        C = rgb.shape[-1]
+        if d_features is None:
+            d_features = torch.zeros(R, C, device=rgb.device)
+        d_sigma = torch.empty_like(raw_density)
+        d_rgb = torch.empty_like(rgb)
+        opt = lambda t: None if t is None else N.f32c(t)
+        N.check(
+            N.lib().yn_composite_bwd(
+                ctypes.byref(ctx.cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
+                N.ptr(bg), N.ptr(N.f32c(d_features)), N.ptr(opt(d_depths)), N.ptr(opt(d_opacities)),
+                N.ptr(opt(d_weights)), N.ptr(d_sigma), N.ptr(d_rgb), R, P, C, N.stream_ptr(),
+            )
+        )
+        return d_sigma, d_rgb, None, None, None, None, None
+
+
+def _copy_cfg(cfg: N.MarchCfg) -> N.MarchCfg:
+    out = N.MarchCfg()
+    ctypes.memmove(ctypes.byref(out), ctypes.byref(cfg), ctypes.sizeof(N.MarchCfg))
+    return out
+
+
+def composite(raw_density, rgb, lengths, directions, cfg: N.MarchCfg, noise=None, bg=None):
+    """raw_density [R,P], rgb [R,P,C], lengths [R,P], directions [R,3] -> features [R,C], depths [R,1],
+    opacities [R,1], weights [R,P]."""
+    if raw_density.shape[0] == 0:
+        R, P = lengths.shape
+        z = lengths.new_zeros
+        return z(R, rgb.shape[-1]), z(R, 1), z(R, 1), z(R, P)
+    return CompositeFunction.apply(raw_density, rgb, lengths, directions, noise, bg, cfg)
+
+
+# --------------------------------------------------------------------------- #
+# inverse-CDF resampling + merge
+# --------------------------------------------------------------------------- #
+_LINSPACE_CACHE = {}
+
+
+def det_draws(n: int, device) -> torch.Tensor:
+    """`torch.linspace(0, 1, n)` exactly as the reference's --device cpu path computes it
+    (renderers/utils.py:130-132); evaluated on the CPU once per (n, device) and cached."""
+    key = (n, str(device))
+    if key not in _LINSPACE_CACHE:
+        _LINSPACE_CACHE[key] = torch.linspace(0.0, 1.0, n, dtype=torch.float32).to(device)
+    return _LINSPACE_CACHE[key]
+
+
+def sample_pdf_merge(lengths: torch.Tensor, weights: torch.Tensor, n_new: int, u: Optional[torch.Tensor],
+                     add_input_samples: bool = True, want_inds: bool = False, flag: Optional[torch.Tensor] = None):
+    """lengths [R,P], weights [R,P] -> sorted new lengths [R, n_new (+P)], inds [R,n_new] int64 or None,
+    flag int32[1] (1 if any weight + 1e-5 <= 0)."""
+    R, P = lengths.shape
+    dev = lengths.device
+    out = torch.empty(R, n_new + (P if add_input_samples else 0), device=dev)
+    inds = torch.empty(R, n_new, dtype=torch.int64, device=dev) if want_inds else None
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if R == 0:
+        return out, inds, flag
+    if u is None:
+        u, stride = det_draws(n_new, dev), 0
+    else:
+        u = N.f32c(u)
+        assert u.shape == (R, n_new), (u.shape, (R, n_new))
+        stride = n_new
+    N.check(
+        N.lib().yn_sample_pdf_merge(
+            N.ptr(N.f32c(lengths)), N.ptr(N.f32c(weights)), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
+            N.ptr(flag, torch.int32), R, P, n_new, int(add_input_samples), N.stream_ptr(),
+        )
+    )
+    return out, inds, flag
+
+
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Optional[torch.Tensor],
+               want_inds: bool = False):
+    """`sample_pdf_python` on explicit bins [R,nb] / weights [R,nb-1] -> samples [R,n] in draw order."""
+    R, nb = bins.shape
+    dev = bins.device
+    out = torch.empty(R, n_samples, device=dev)
+    inds = torch.empty(R, n_samples, dtype=torch.int64, device=dev) if want_inds else None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if R == 0:
+        return out, inds, flag
+    if u is None:
+        u, stride = det_draws(n_samples, dev), 0
+    else:
+        u, stride = N.f32c(u), n_samples
+    N.check(
+        N.lib().yn_sample_pdf(
+            N.ptr(N.f32c(bins)), N.ptr(N.f32c(weights)), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
+            N.ptr(flag, torch.int32), R, nb, n_samples, N.stream_ptr(),
+        )
+    )
+    return out, inds, flag
+
+
+# --------------------------------------------------------------------------- #
+# optimizer
+# --------------------------------------------------------------------------- #
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    N.check(
+        N.lib().yn_adam_step(
+            N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
+            int(step), grad_scale, N.stream_ptr(),
+        )
+    )

@@ -1,0 +1,180 @@
+"""NeRFMLP: harmonic embedding + 8x256 skip trunk + density and view-dependent colour heads.
+
+Same registry name, constructor keywords (including the reference's spellings), forward signature,
+output dict and state-dict keys as `yanerf/pipelines/models/nerf_mlp.py:12-183`, so reference configs and
+checkpoints load unchanged.  The torch sub-modules below only HOLD the parameters under the reference's
+names; the arithmetic of `forward` is the fused sm_100a kernel chain (`yn_mlp_dirbias`, `yn_mlp_fwd`,
+`yn_mlp_bwd`): there is no torch implementation of the network in this package.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional
+
+import torch
+
+from yanerf import _native as N
+from yanerf import ops
+from yanerf.utils.logging import get_logger
+
+from .builder import MODELS
+
+
+class LinearWithRepeat(torch.nn.Module):
+    """Parameter holder of the colour hidden layer (models/utils.py:135-211): weight [out, n1 + n2]."""
+
+    def __init__(self, in_features: int, out_features: int) -> None:
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = torch.nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = torch.nn.Parameter(torch.empty(out_features))
+        torch.nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1 / math.sqrt(in_features)
+        torch.nn.init.uniform_(self.bias, -bound, bound)
+
+
+class MLPWithInputSkips(torch.nn.Module):
+    """Parameter holder of the trunk (nerf_mlp.py:186-289): `mlp.{l}.0` = Linear, `mlp.{l}.1` = ReLU.
+    Inner width is always `hidden_dim` = 256; only the last layer emits `output_dim` (nerf_mlp.py:88-95)."""
+
+    def __init__(self, n_layers: int, input_dim: int, output_dim: int, skip_dim: int, input_skips, hidden_dim: int = 256):
+        super().__init__()
+        layers = []
+        for li in range(n_layers):
+            din = input_dim if li == 0 else (hidden_dim + skip_dim if li in input_skips else hidden_dim)
+            dout = hidden_dim if li + 1 < n_layers else output_dim
+            lin = torch.nn.Linear(din, dout)
+            torch.nn.init.xavier_uniform_(lin.weight.data)
+            layers.append(torch.nn.Sequential(lin, torch.nn.ReLU(True)))
+        self.mlp = torch.nn.ModuleList(layers)
+        self._input_skips = set(input_skips)
+
+
+def _default_fmt() -> int:
+    return {"fp16": N.FMT_FP16, "bf16": N.FMT_BF16}[os.environ.get("YANERF_MLP_DTYPE", "fp16").lower()]
+
+
+@MODELS.register_module()
+class NeRFMLP(torch.nn.Module):
+    def __init__(
+        self,
+        n_layers: int = 8,
+        input_skips: List[int] = [5],
+        n_harmonic_functions_xyz: int = 10,
+        harmonic_functions_xyz_append_intput: bool = True,
+        n_hidden_neurons_xyz: int = 256,
+        n_harmonic_functions_dir: int = 4,
+        harmonic_functions_dir_append_intput: bool = True,
+        n_hidden_neurons_dir: int = 128,
+        latent_dim: int = 0,
+        input_xyz: bool = True,
+        input_dir: bool = True,
+        color_dim: int = 3,
+        nerf_paper_v1=False,
+    ) -> None:
+        super().__init__()
+        self.logger = get_logger(__name__)
+        if not input_xyz and latent_dim <= 0:
+            raise ValueError("The latent dimension has to be > 0 if xyz is not input!")
+        unsupported = []
+        if latent_dim > 0:
+            unsupported.append("latent_dim > 0 (global_codes)")
+        if not input_xyz or not input_dir:
+            unsupported.append("input_xyz / input_dir = False")
+        if not harmonic_functions_xyz_append_intput or not harmonic_functions_dir_append_intput:
+            unsupported.append("harmonic embedding without the appended input")
+        if nerf_paper_v1:
+            unsupported.append("nerf_paper_v1 extra colour layers")
+        if unsupported:
+            raise NotImplementedError(
+                "the sm_100a NeRF-MLP kernel covers the lego.yml / fern.yml architecture family only; unsupported: "
+                + ", ".join(unsupported)
+            )
+        self.n_layers = n_layers
+        self.input_skips = list(input_skips)
+        self.n_harmonic_functions_xyz = n_harmonic_functions_xyz
+        self.harmonic_functions_xyz_append_intput = harmonic_functions_xyz_append_intput
+        self.n_hidden_neurons_xyz = n_hidden_neurons_xyz
+        self.n_harmonic_functions_dir = n_harmonic_functions_dir
+        self.harmonic_functions_dir_append_intput = harmonic_functions_dir_append_intput
+        self.n_hidden_neurons_dir = n_hidden_neurons_dir
+        self.latent_dim = latent_dim
+        self.input_xyz, self.input_dir = input_xyz, input_dir
+        self.color_dim = color_dim
+
+        embed_xyz = 3 * (2 * n_harmonic_functions_xyz + 1)
+        embed_dir = 3 * (2 * n_harmonic_functions_dir + 1)
+        self.xyz_encoder = MLPWithInputSkips(n_layers, embed_xyz, n_hidden_neurons_xyz, embed_xyz, self.input_skips)
+        self.intermediate_linear = torch.nn.Linear(n_hidden_neurons_xyz, n_hidden_neurons_xyz)
+        torch.nn.init.xavier_uniform_(self.intermediate_linear.weight.data)
+        self.density_layer = torch.nn.Linear(n_hidden_neurons_xyz, 1)
+        torch.nn.init.xavier_uniform_(self.density_layer.weight.data)
+        self.density_layer.bias.data[:] = 0.0
+        self.color_layer = torch.nn.Sequential(
+            LinearWithRepeat(n_hidden_neurons_xyz + embed_dir, n_hidden_neurons_dir),
+            torch.nn.ReLU(True),
+            torch.nn.Linear(n_hidden_neurons_dir, color_dim),
+            torch.nn.Sigmoid(),
+        )
+
+        skip_mask = 0
+        for li in self.input_skips:
+            if 0 < li < n_layers:
+                skip_mask |= 1 << li
+        self._arch = N.MlpArch(n_layers, skip_mask, n_harmonic_functions_xyz, n_harmonic_functions_dir,
+                               n_hidden_neurons_xyz, n_hidden_neurons_dir, color_dim, _default_fmt())
+        self._plan: Optional[ops.MlpPlan] = None
+        self._packed_key = None
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def ordered_parameters(self) -> List[torch.nn.Parameter]:
+        """State-dict order = the flat layout `yn_mlp_pack_weights` expects."""
+        ps: List[torch.nn.Parameter] = []
+        for seq in self.xyz_encoder.mlp:
+            ps += [seq[0].weight, seq[0].bias]
+        ps += [self.intermediate_linear.weight, self.intermediate_linear.bias]
+        ps += [self.density_layer.weight, self.density_layer.bias]
+        ps += [self.color_layer[0].weight, self.color_layer[0].bias, self.color_layer[2].weight, self.color_layer[2].bias]
+        return ps
+
+    def set_operand_dtype(self, name: str) -> None:
+        """'bf16' or 'fp16' tensor-core operands (fp32 accumulation either way)."""
+        self._arch.fmt = {"fp16": N.FMT_FP16, "bf16": N.FMT_BF16}[name]
+        self._packed_key = None
+
+    def _flat(self) -> torch.Tensor:
+        return torch.cat([p.reshape(-1) for p in self.ordered_parameters()])
+
+    def plan_for(self, flat: torch.Tensor) -> ops.MlpPlan:
+        """(Re)pack the tensor-core weight image when the parameters changed since the last call."""
+        ps = self.ordered_parameters()
+        key = (self._arch.fmt, str(flat.device)) + tuple((p.data_ptr(), p._version) for p in ps)
+        if self._plan is None or self._plan.wpack.device != flat.device:
+            self._plan = ops.MlpPlan.create(self._arch, flat.device)
+            self._packed_key = None
+        if key != self._packed_key:
+            self._plan.pack(flat.detach())
+            self._packed_key = key
+        return self._plan
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, origins: torch.Tensor, directions: torch.Tensor, lengths: torch.Tensor,
+                global_codes: Optional[torch.Tensor] = None, **kwargs) -> dict:
+        """origins/directions `[B,*sp,3]`, lengths `[B,*sp,P]` -> rays_densities `[B,*sp,P,1]` (raw),
+        rays_features `[B,*sp,P,color_dim]`, aux {}."""
+        if global_codes is not None:
+            raise ValueError("The shape of global codes is imcompible with the input dim of the network.")
+        lead = lengths.shape[:-1]
+        P = lengths.shape[-1]
+        flat = self._flat()
+        plan = self.plan_for(flat)
+        o = N.f32c(origins.expand(*lead, 3)).reshape(-1, 3)
+        d = N.f32c(directions.expand(*lead, 3)).reshape(-1, 3)
+        z = N.f32c(lengths).reshape(-1, P)
+        density, rgb = ops.MlpFunction.apply(flat, o, d, z, plan)
+        return dict(
+            rays_densities=density.reshape(*lead, P, 1),
+            rays_features=rgb.reshape(*lead, P, self.color_dim),
+            aux={},
+        )
