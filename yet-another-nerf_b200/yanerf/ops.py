@@ -15,6 +15,43 @@ import torch
 from . import _native as N
 
 
+class Profiler:
+    """Optional per-kernel CUDA-event timing (bench.py / tools): events are recorded on the launching
+    stream around each C-ABI call; `launches` counts device kernels launched by this package."""
+
+    enabled = False
+    records: list = []
+    launches = 0
+    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 2}
+
+    @classmethod
+    def reset(cls):
+        cls.records, cls.launches = [], 0
+
+    @classmethod
+    def summary(cls):
+        """name -> (calls, total ms); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, s, e in cls.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + s.elapsed_time(e))
+        return out
+
+
+def _call(name: str, *args) -> None:
+    fn = getattr(N.lib(), name)
+    if Profiler.enabled:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        Profiler.records.append((name, s, e))
+    else:
+        rc = fn(*args)
+    Profiler.launches += Profiler.KERNELS_PER_CALL.get(name, 1)
+    N.check(rc)
+
+
 # --------------------------------------------------------------------------- #
 # ray sampler
 # --------------------------------------------------------------------------- #
@@ -47,14 +84,12 @@ def ray_bundle(
     directions = torch.empty(B, n_rays, 3, device=dev)
     lengths = torch.empty(B, n_rays, P, device=dev)
     xys = torch.empty(B, n_rays, 2, device=dev) if full else xy
-    N.check(
-        N.lib().yn_ray_bundle(
+    _call("yn_ray_bundle", 
             ctypes.c_void_p(poses.data_ptr()), poses.stride(0), poses.stride(1), N.ptr(focal), N.ptr(xy),
             N.ptr(N.f32c(depths)), N.ptr(None if u is None else N.f32c(u)), N.ptr(origins), N.ptr(directions),
             N.ptr(lengths), N.ptr(xys if full else None), B, n_rays, P, width, height, 1 if full else 0,
             N.stream_ptr(),
         )
-    )
     return origins, directions, lengths, xys
 
 
@@ -87,11 +122,9 @@ class MlpPlan:
 
     def pack(self, flat_params: torch.Tensor) -> None:
         assert flat_params.numel() == self.n_params
-        N.check(
-            N.lib().yn_mlp_pack_weights(
+        _call("yn_mlp_pack_weights", 
                 ctypes.byref(self.arch), N.ptr(flat_params), N.ptr(self.wpack, torch.uint8), N.ptr(self.aux), N.stream_ptr()
             )
-        )
 
 
 def mlp_forward_raw(
@@ -108,14 +141,12 @@ def mlp_forward_raw(
         return density, rgb
     dirbias = torch.empty(R, 128, device=dev)
     L = N.lib()
-    N.check(L.yn_mlp_dirbias(ctypes.byref(plan.arch), N.ptr(flat_params), N.ptr(directions), N.ptr(dirbias), R, N.stream_ptr()))
-    N.check(
-        L.yn_mlp_fwd(
+    _call("yn_mlp_dirbias", ctypes.byref(plan.arch), N.ptr(flat_params), N.ptr(directions), N.ptr(dirbias), R, N.stream_ptr())
+    _call("yn_mlp_fwd", 
             ctypes.byref(plan.arch), N.ptr(origins), N.ptr(directions), N.ptr(lengths), N.ptr(dirbias),
             N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(density), N.ptr(rgb),
             N.ptr(stash, torch.uint8), R, P, N.stream_ptr(),
         )
-    )
     return density, rgb
 
 
@@ -150,13 +181,11 @@ class MlpFunction(torch.autograd.Function):
             d_rgb = N.f32c(d_rgb) if d_rgb is not None else torch.zeros_like(rgb)
             wbytes = L.yn_mlp_bwd_workspace_bytes(ctypes.byref(plan.arch), R * P)
             work = torch.empty(int(wbytes), dtype=torch.uint8, device=rgb.device)
-            N.check(
-                L.yn_mlp_bwd(
+            _call("yn_mlp_bwd", 
                     ctypes.byref(plan.arch), N.ptr(directions), N.ptr(rgb), N.ptr(d_density), N.ptr(d_rgb),
                     N.ptr(flat_params), N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(ctx.stash, torch.uint8),
                     N.ptr(work, torch.uint8), N.ptr(grads), R, P, N.stream_ptr(),
                 )
-            )
         ctx.stash = None
         return grads, None, None, None, None
 
@@ -196,12 +225,10 @@ class CompositeFunction(torch.autograd.Function):
         depths = torch.empty(R, 1, device=dev)
         opacities = torch.empty(R, 1, device=dev)
         weights = torch.empty(R, P, device=dev)
-        N.check(
-            N.lib().yn_composite_fwd(
+        _call("yn_composite_fwd", 
                 ctypes.byref(cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
                 N.ptr(bg), N.ptr(features), N.ptr(depths), N.ptr(opacities), N.ptr(weights), R, P, C, N.stream_ptr(),
             )
-        )
         ctx.cfg = cfg
         ctx.has = (noise is not None, bg is not None)
         saved = [raw_density, rgb, lengths, directions] + ([noise] if noise is not None else []) + ([bg] if bg is not None else [])
@@ -222,13 +249,11 @@ class CompositeFunction(torch.autograd.Function):
         d_sigma = torch.empty_like(raw_density)
         d_rgb = torch.empty_like(rgb)
         opt = lambda t: None if t is None else N.f32c(t)
-        N.check(
-            N.lib().yn_composite_bwd(
+        _call("yn_composite_bwd", 
                 ctypes.byref(ctx.cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
                 N.ptr(bg), N.ptr(N.f32c(d_features)), N.ptr(opt(d_depths)), N.ptr(opt(d_opacities)),
                 N.ptr(opt(d_weights)), N.ptr(d_sigma), N.ptr(d_rgb), R, P, C, N.stream_ptr(),
             )
-        )
         return d_sigma, d_rgb, None, None, None, None, None
 
 
@@ -281,12 +306,10 @@ def sample_pdf_merge(lengths: torch.Tensor, weights: torch.Tensor, n_new: int, u
         u = N.f32c(u)
         assert u.shape == (R, n_new), (u.shape, (R, n_new))
         stride = n_new
-    N.check(
-        N.lib().yn_sample_pdf_merge(
+    _call("yn_sample_pdf_merge", 
             N.ptr(N.f32c(lengths)), N.ptr(N.f32c(weights)), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
             N.ptr(flag, torch.int32), R, P, n_new, int(add_input_samples), N.stream_ptr(),
         )
-    )
     return out, inds, flag
 
 
@@ -304,12 +327,10 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Opt
         u, stride = det_draws(n_samples, dev), 0
     else:
         u, stride = N.f32c(u), n_samples
-    N.check(
-        N.lib().yn_sample_pdf(
+    _call("yn_sample_pdf", 
             N.ptr(N.f32c(bins)), N.ptr(N.f32c(weights)), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
             N.ptr(flag, torch.int32), R, nb, n_samples, N.stream_ptr(),
         )
-    )
     return out, inds, flag
 
 
@@ -317,9 +338,7 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Opt
 # optimizer
 # --------------------------------------------------------------------------- #
 def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-    N.check(
-        N.lib().yn_adam_step(
+    _call("yn_adam_step", 
             N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
             int(step), grad_scale, N.stream_ptr(),
         )
-    )
