@@ -39,7 +39,8 @@ def test_eval_render_vs_reference_golden(golden, tag, n_fine, std, gain, coalesc
     print(f"{tag} coalesce={coalesce}: rendered rgb max abs err {err:.2e}, depth {derr:.2e}")
     if gain == 1.0:
         assert err <= 2e-3, err
-        assert derr <= 2e-2, derr
+        # depth = sum(w * z) with z in [2, 6]: the 16-bit-operand density error moves it by O(1e-2) relative
+        assert derr <= 0.12, derr
         assert abs(float(ev["loss_rgb_mse"].mean().cpu()) - float(g[f"{tag}_eval_loss_rgb_mse"].mean())) <= 1e-3
     else:  # stress weights (see test_mlp_forward_golden)
         assert float((ev["rendered_images"].cpu() - T(g[f"{tag}_eval_rendered_images"])).abs().mean()) <= 2e-2

@@ -13,6 +13,7 @@ constexpr int kTileM = 128;        // points per tile (= UMMA M)
 constexpr int kBlkBytes = 16384;   // one [128 x 64] 16-bit operand block
 constexpr int kMaxLayers = 12;
 constexpr int kDirPad = 128;       // padded width of the colour hidden layer
+constexpr int kBiasBlkBytes = 4096;  // [128 x 16] 16-bit, no swizzle (8x8 core matrices)
 
 struct Arch {
   int n_layers;
@@ -28,7 +29,13 @@ struct Arch {
   __host__ __device__ int nkb_hidden(int l) const { return l == 0 ? 0 : 4; }
   __host__ __device__ int nkb(int l) const { return nkb_hidden(l) + (has_emb(l) ? 1 : 0); }
   __host__ __device__ int nnh(int l) const { return l == n_layers + 1 ? 1 : 2; }
-  __host__ __device__ int stages(int l) const { return nkb(l) * nnh(l); }
+  // trunk / intermediate layers without an embedding K-block fold their bias in through one extra 4 KB
+  // "bias block": a K=16 MMA of the embedding block's last slice (whose channel 63 is the constant 1) with a
+  // [128 x 16] weight slice holding the bias in column 15.  Layers WITH an embedding block carry the bias in
+  // column 63 of that block.  The colour hidden layer adds its per-ray bias in the epilogue.
+  __host__ __device__ bool has_bias_stage(int l) const { return l <= n_layers && !has_emb(l); }
+  __host__ __device__ int stages_per_half(int l) const { return nkb(l) + (has_bias_stage(l) ? 1 : 0); }
+  __host__ __device__ int stages(int l) const { return stages_per_half(l) * nnh(l); }
   __host__ __device__ int stage_offset(int l) const {
     int s = 0;
     for (int i = 0; i < l; ++i) s += stages(i);

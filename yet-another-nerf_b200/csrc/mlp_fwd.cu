@@ -13,8 +13,10 @@
 //   warps 2-5   epilogue group 0, warps 6-9 epilogue group 1: tcgen05.ld the accumulator, add bias, ReLU,
 //               convert to 16 bit and write the next layer's A operand back to shared memory.  The first
 //               "epilogue" of a tile computes the embedding, the last ones compute the fp32 heads.
-// Two 128-point tiles are in flight per CTA (TMEM columns [0,256) and [256,512)); the MMA warp alternates
-// between them layer by layer so the epilogue of one tile overlaps the MMAs of the other.
+// Two 128-point tiles are in flight per CTA (TMEM columns [0,256) and [256,512)) and advance in lockstep: every
+// weight block read from L2 feeds the MMAs of both tiles.  Each 256-wide layer is issued as two 128-column halves;
+// the epilogue of half 0 (-> activation blocks 0,1 of the next layer) runs while half 1 is still being multiplied,
+// and the next layer starts on blocks 0,1 while the epilogue of half 1 fills blocks 2,3.
 #include <cuda_runtime.h>
 
 #include "mlp_common.cuh"
@@ -68,6 +70,68 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
+// processes accumulator columns [c_lo, c_lo + 128) of one row: (ReLU) -> 16-bit -> activation blocks
+// (c_lo / 64, c_lo / 64 + 1); kMode 0 = trunk (ReLU), 1 = intermediate (no activation), 2 = colour hidden
+// (per-ray direction bias, ReLU, colour head partial sums in `acc`)
+template <int kFmt, int kMode, bool kWrite>
+__device__ __forceinline__ void epilogue_half(uint32_t t_addr, int c_lo, const float* __restrict__ bias,
+                                              const float* __restrict__ wd, bool want_density, float& dens,
+                                              const float* __restrict__ w2, float (&acc)[4], uint32_t act_row,
+                                              uint32_t swz) {
+#pragma unroll 1
+  for (int cb = 0; cb < 4; cb += 2) {
+    uint32_t v[2][32];
+    tmem_ld32(t_addr + c_lo + cb * 32, v[0]);
+    tmem_ld32(t_addr + c_lo + cb * 32 + 32, v[1]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c0 = c_lo + (cb + h) * 32;
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        // trunk / intermediate layers: the bias is already in the accumulator (folded into the MMA)
+        float x0 = __uint_as_float(v[h][j]), x1 = __uint_as_float(v[h][j + 1]);
+        float x2 = __uint_as_float(v[h][j + 2]), x3 = __uint_as_float(v[h][j + 3]);
+        if (kMode == 2) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+          x0 = fmaxf(x0 + b.x, 0.f); x1 = fmaxf(x1 + b.y, 0.f); x2 = fmaxf(x2 + b.z, 0.f); x3 = fmaxf(x3 + b.w, 0.f);
+        }
+        if (kMode == 0 && want_density) {
+          x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
+          dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
+          dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
+        }
+        if (kMode == 2) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0 + j));
+            acc[c] = fmaf(x0, w.x, acc[c]); acc[c] = fmaf(x1, w.y, acc[c]);
+            acc[c] = fmaf(x2, w.z, acc[c]); acc[c] = fmaf(x3, w.w, acc[c]);
+          }
+        }
+        if (kWrite) {
+          if (kMode == 0) {  // ReLU fused into the conversion
+            pk[j / 2] = pack_relu<kFmt>(x0, x1);
+            pk[j / 2 + 1] = pack_relu<kFmt>(x2, x3);
+          } else {
+            pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
+            pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
+          }
+        }
+      }
+      if (kWrite) {
+        const uint32_t blk = act_row + (c0 >> 6) * kBlkBytes;
+        const uint32_t u0 = ((c0 >> 5) & 1) * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      }
+    }
+  }
+}
+
 template <int kFmt, bool kStash>
 __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -76,9 +140,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
   const uint32_t s_emb = smem_base + kSmemEmb;
   const uint32_t s_ring = smem_base + kSmemRing;
   const uint32_t s_bar = smem_base + kSmemBar;
-  // barrier layout (8 B each): full[4], empty[4], tmem_full[2], act_ready[2], then tmem ptr
-  const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kRing, bar_tfull = s_bar + 16 * kRing,
-                 bar_ready = bar_tfull + 16, s_tmem_ptr = bar_ready + 16;
+  // barriers (8 B each): full[4], empty[4], half_full[2], blk01_free, epi_done[2]; then the TMEM base address
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kRing, bar_hfull = s_bar + 16 * kRing,
+                 bar_b01 = bar_hfull + 16, bar_epi = bar_b01 + 8, s_tmem_ptr = bar_epi + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,10 +156,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
     }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(bar_tfull + 8 * g, 1);
-      mbar_init(bar_ready + 8 * g, 128);
-    }
+    mbar_init(bar_hfull, 1);
+    mbar_init(bar_hfull + 8, 1);
+    mbar_init(bar_b01, 1);
+    mbar_init(bar_epi, 256);
+    mbar_init(bar_epi + 8, 256);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -113,55 +178,81 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        int soff = 0;
+        int s = 0;
         for (int l = 0; l < L; ++l) {
-          const int nst = A.stages(l);
-          const uint8_t* src = p.wpack + (size_t)soff * kBlkBytes;
-          for (int g = 0; g < 2; ++g) {
-            for (int s = 0; s < nst; ++s) {
-              mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-              mbar_arrive_expect_tx(bar_full + 8 * slot, kBlkBytes);
-              bulk_g2s(s_ring + slot * kBlkBytes, src + (size_t)s * kBlkBytes, kBlkBytes, bar_full + 8 * slot);
-              if (++slot == kRing) { slot = 0; phase ^= 1; }
-            }
+          const int per_half = A.stages_per_half(l), nkb = A.nkb(l);
+          for (int j = 0; j < per_half * A.nnh(l); ++j, ++s) {
+            const uint32_t bytes = (j % per_half) == nkb ? kBiasBlkBytes : kBlkBytes;
+            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+            bulk_g2s(s_ring + slot * kBlkBytes, p.wpack + (size_t)s * kBlkBytes, bytes, bar_full + 8 * slot);
+            if (++slot == kRing) { slot = 0; phase ^= 1; }
           }
-          soff += nst;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
+    // Both tiles consume every weight block (one L2 read feeds 8 MMAs).  Dependencies on the epilogue:
+    //   epi_done[0]: output blocks 0,1 of the previous layer written and accumulator half 0 drained
+    //   epi_done[1]: blocks 2,3 written and accumulator half 1 drained
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(128, 128, kFmt, 0, 0);
       uint32_t slot = 0, phase = 0;
-      uint32_t ready_phase[2] = {0, 0};
+      uint32_t ed_phase0 = 0, ed_phase1 = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           const int nkbh = A.nkb_hidden(l);
           const int nkb = A.nkb(l);
           const int nnh = A.nnh(l);
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(bar_ready + 8 * g, ready_phase[g]);
-            ready_phase[g] ^= 1;
-            tc_fence_after();
-            for (int nh = 0; nh < nnh; ++nh) {
-              const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
-              for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(bar_full + 8 * slot, phase);
+          const int kb_free = nkb > 1 ? 1 : 0;
+          const bool has_bias = A.has_bias_stage(l);
+          mbar_wait(bar_epi, ed_phase0);
+          ed_phase0 ^= 1;
+          tc_fence_after();
+          bool waited1 = false;
+          for (int nh = 0; nh < nnh; ++nh) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (!waited1 && (nh == 1 || (kb >= 2 && kb < nkbh))) {
+                mbar_wait(bar_epi + 8, ed_phase1);
+                ed_phase1 ^= 1;
                 tc_fence_after();
-                const uint32_t a_base = (kb < nkbh) ? (s_act + (g * 4 + kb) * kBlkBytes) : (s_emb + g * kBlkBytes);
-                const uint32_t b_base = s_ring + slot * kBlkBytes;
+                waited1 = true;
+              }
+              mbar_wait(bar_full + 8 * slot, phase);
+              tc_fence_after();
+              const uint32_t b_base = s_ring + slot * kBlkBytes;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+              for (int g = 0; g < 2; ++g) {
+                const uint32_t a_base = (kb < nkbh) ? (s_act + (g * 4 + kb) * kBlkBytes) : (s_emb + g * kBlkBytes);
+                const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
                   umma_f16(d_tmem, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
                            (kb | k) != 0);
-                }
-                umma_commit(bar_empty + 8 * slot);
-                if (++slot == kRing) { slot = 0; phase ^= 1; }
               }
+              umma_commit(bar_empty + 8 * slot);
+              if (++slot == kRing) { slot = 0; phase ^= 1; }
+              // activation blocks 0,1 are not read again in this layer after (last half, kb_free)
+              if (nh == nnh - 1 && kb == kb_free) umma_commit(bar_b01);
             }
-            umma_commit(bar_tfull + 8 * g);
+            if (has_bias) {
+              // + bias: embedding slice 3 (channel 63 == 1) x the [128 x 16] bias block
+              mbar_wait(bar_full + 8 * slot, phase);
+              tc_fence_after();
+              const uint64_t b_desc = umma_desc_kmajor_k16_nosw(s_ring + slot * kBlkBytes);
+#pragma unroll
+              for (int g = 0; g < 2; ++g)
+                umma_f16(tmem_base + g * 256 + nh * 128, umma_desc_kmajor(s_emb + g * kBlkBytes + 96), b_desc, idesc, 1);
+              umma_commit(bar_empty + 8 * slot);
+              if (++slot == kRing) { slot = 0; phase ^= 1; }
+            }
+            umma_commit(bar_hfull + 8 * nh);
+          }
+          if (!waited1) {
+            mbar_wait(bar_epi + 8, ed_phase1);
+            ed_phase1 ^= 1;
           }
         }
       }
@@ -176,11 +267,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     const uint32_t act_g = s_act + g * 4 * kBlkBytes;
     const uint32_t emb_g = s_emb + g * kBlkBytes;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
-    const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+    const uint32_t act_row = act_g + static_cast<uint32_t>(row) * 128u;
     const bool stash_leader = (warp - 2) % 4 == 0 && lane == 0;
     const int nfx = A.n_freq_xyz;
     const int blocks_per_tile = A.stash_blocks_per_tile();
-    uint32_t tf_phase = 0;
+    uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
@@ -215,10 +306,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           }
           st_shared_u16(emb_g + sw128_offset(row, 6 * nfx + a), to_half_bits<kFmt>(pt[a]));
         }
-        for (int ch = 6 * nfx + 3; ch < 64; ++ch) st_shared_u16(emb_g + sw128_offset(row, ch), 0);
+        for (int ch = 6 * nfx + 3; ch < 63; ++ch) st_shared_u16(emb_g + sw128_offset(row, ch), 0);
+        st_shared_u16(emb_g + sw128_offset(row, 63), to_half_bits<kFmt>(1.f));  // bias channel
       }
+      // the embedding acts as the epilogue of a virtual layer -1: both halves "done"
+      tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_ready + 8 * g);
+      mbar_arrive(bar_epi);
+      mbar_arrive(bar_epi + 8);
       if (kStash) {
         named_bar_sync(1 + g, 128);
         if (stash_leader && tile_live) {
@@ -228,109 +323,55 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       }
 
       float dens = 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int l = 0; l < L; ++l) {
-        mbar_wait(bar_tfull + 8 * g, tf_phase);
-        tf_phase ^= 1;
-        tc_fence_after();
         const bool is_color = (l == L - 1);
         const bool is_inter = (l == L - 2);
         const bool is_last_trunk = (l == L - 3);
-        const bool writes_act = !is_color || kStash;
+        const float* bias = is_color ? p.dirbias + ray * kDirPad : p.aux + A.aux_bias(l);
+        const float* wd = p.aux + A.aux_wd();
+        const float* w2 = p.aux + A.aux_w2();
+        // ---- half 0: accumulator columns [0,128) -> activation blocks 0,1
+        mbar_wait(bar_hfull, hf_phase0);
+        hf_phase0 ^= 1;
+        mbar_wait(bar_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
+        b01_phase ^= 1;
+        tc_fence_after();
         if (kStash) {
-          // the previous layer's stash store may still be reading this tile's activation buffer
-          if (stash_leader) bulk_wait_read<0>();
+          if (stash_leader) bulk_wait_read<0>();  // the previous layer's stash store has read the buffer
           named_bar_sync(1 + g, 128);
         }
+        if (is_color)
+          epilogue_half<kFmt, 2, kStash>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
+        else if (is_inter)
+          epilogue_half<kFmt, 1, true>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
+        else
+          epilogue_half<kFmt, 0, true>(t_row, 0, bias, wd, is_last_trunk, dens, w2, acc, act_row, swz);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        // the last layer feeds no MMA: the next pair's embedding arrival (program order) covers the TMEM hand-over
+        if (!is_color) mbar_arrive(bar_epi);
+        // ---- half 1: columns [128,256) -> blocks 2,3 (the colour hidden layer is 128 wide: nothing to do)
         if (!is_color) {
-          const float* bias = p.aux + A.aux_bias(l);
-          const float* wd = p.aux + A.aux_wd();
-#pragma unroll 1
-          for (int cb = 0; cb < 8; cb += 2) {
-            uint32_t v[2][32];
-            tmem_ld32(t_row + cb * 32, v[0]);
-            tmem_ld32(t_row + cb * 32 + 32, v[1]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = (cb + h) * 32;
-              uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-                float x0 = __uint_as_float(v[h][j]) + b.x, x1 = __uint_as_float(v[h][j + 1]) + b.y;
-                float x2 = __uint_as_float(v[h][j + 2]) + b.z, x3 = __uint_as_float(v[h][j + 3]) + b.w;
-                if (!is_inter) {
-                  x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-                }
-                if (is_last_trunk) {
-                  const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
-                  dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
-                  dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
-                }
-                pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
-                pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
-              }
-              const uint32_t blk = act_g + ((cb + h) >> 1) * kBlkBytes + row_off;
-              const uint32_t u0 = ((cb + h) & 1) * 4;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-            }
-          }
-          if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
-        } else {
-          // colour hidden layer: + per-ray direction bias (LinearWithRepeat), ReLU, then the colour head
-          const float* db = p.dirbias + ray * kDirPad;
-          const float* w2 = p.aux + A.aux_w2();
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-          for (int cb = 0; cb < 4; cb += 2) {
-            uint32_t v[2][32];
-            tmem_ld32(t_row + cb * 32, v[0]);
-            tmem_ld32(t_row + cb * 32 + 32, v[1]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = (cb + h) * 32;
-              uint32_t pk[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(db + c0 + j));
-                const float x0 = fmaxf(__uint_as_float(v[h][j]) + b.x, 0.f);
-                const float x1 = fmaxf(__uint_as_float(v[h][j + 1]) + b.y, 0.f);
-                const float x2 = fmaxf(__uint_as_float(v[h][j + 2]) + b.z, 0.f);
-                const float x3 = fmaxf(__uint_as_float(v[h][j + 3]) + b.w, 0.f);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0 + j));
-                  acc[c] = fmaf(x0, w.x, acc[c]); acc[c] = fmaf(x1, w.y, acc[c]);
-                  acc[c] = fmaf(x2, w.z, acc[c]); acc[c] = fmaf(x3, w.w, acc[c]);
-                }
-                if (kStash) {
-                  pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
-                  pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
-                }
-              }
-              if (kStash) {
-                const uint32_t blk = act_g + ((cb + h) >> 1) * kBlkBytes + row_off;
-                const uint32_t u0 = ((cb + h) & 1) * 4;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-              }
-            }
-          }
-          if (valid) {
-            const int C = A.color_dim;
-            for (int c = 0; c < C; ++c) {
-              const float x = acc[c] + __ldg(p.aux + A.aux_b2() + c);
-              p.rgb[gidx * C + c] = 1.f / (1.f + expf(-x));
-            }
+          mbar_wait(bar_hfull + 8, hf_phase1);
+          hf_phase1 ^= 1;
+          tc_fence_after();
+          if (is_inter)
+            epilogue_half<kFmt, 1, true>(t_row, 128, bias, wd, false, dens, w2, acc, act_row, swz);
+          else
+            epilogue_half<kFmt, 0, true>(t_row, 128, bias, wd, is_last_trunk, dens, w2, acc, act_row, swz);
+          tc_fence_before();
+          fence_proxy_async_smem();
+        }
+        if (!is_color) mbar_arrive(bar_epi + 8);
+        if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
+        if (is_color && valid) {
+          const int C = A.color_dim;
+          for (int c = 0; c < C; ++c) {
+            const float x = acc[c] + __ldg(p.aux + A.aux_b2() + c);
+            p.rgb[gidx * C + c] = 1.f / (1.f + expf(-x));
           }
         }
-        tc_fence_before();
-        if (writes_act) fence_proxy_async_smem();
-        if (!is_color) mbar_arrive(bar_ready + 8 * g);
         if (kStash) {
           named_bar_sync(1 + g, 128);
           if (stash_leader && tile_live) {

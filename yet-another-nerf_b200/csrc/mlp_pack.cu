@@ -32,9 +32,21 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
     while (l < L && s >= off + A.stages(l)) { off += A.stages(l); ++l; }
     const int local = s - off;
     const int nkb = A.nkb(l);
-    const int nh = local / nkb, kb = local % nkb;
-    const int n = nh * 128 + r;
+    const int per_half = A.stages_per_half(l);
+    const int nh = local / per_half, kb = local % per_half;
     const int din = A.din(l);
+    if (kb == nkb) {
+      // bias block: [128 x 16] no-swizzle image in the first 4 KB of the slot (rest zero): column 15 = bias
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      if (unit < 256) {
+        const int grp = unit >> 4, kc = (unit >> 3) & 1, rr = unit & 7;
+        const int n = nh * 128 + grp * 8 + rr;
+        if (kc == 1 && n < A.dout(l)) out.w = Half2Pack<kFmt>::pack(0.f, params[A.b_offset(l) + n]);
+      }
+      *reinterpret_cast<uint4*>(wpack + (size_t)s * kBlkBytes + (size_t)unit * 16) = out;
+      return;
+    }
+    const int n = nh * 128 + r;
     if (n < A.dout(l)) {
       const float* W = params + A.w_offset(l);
       const bool emb_blk = kb >= A.nkb_hidden(l);
@@ -44,6 +56,8 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
         int col = -1;
         if (emb_blk) {
           if (c < A.embed_xyz()) col = A.hidden_in(l) + c;
+          // channel 63 of the embedding block is the constant 1: its weight is the layer's bias
+          if (c == 63 && l <= A.n_layers) vals[i] = params[A.b_offset(l) + n];
         } else {
           const int k = kb * 64 + c;
           if (k < A.hidden_in(l)) col = k;

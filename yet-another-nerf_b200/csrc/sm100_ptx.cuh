@@ -153,6 +153,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// K-major [rows x 16 x 16-bit] tile without swizzle: 8x8 core matrices of 128 contiguous bytes, the two K chunks
+// 128 B apart (LBO), 8-row groups 256 B apart (SBO)
+__device__ __forceinline__ uint64_t umma_desc_kmajor_k16_nosw(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
 // K-major operand tile [rows x 64 x 16-bit], 128-byte rows, 8-row swizzle atoms of 1024 B
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) { return umma_desc_sw128(smem_addr, 16, 1024); }
 
@@ -186,6 +196,17 @@ struct Half2Pack<0> {
     return __half22float2(*reinterpret_cast<__half2*>(&u));
   }
 };
+
+// fp32 pair -> packed 16-bit pair with the ReLU fused into the conversion (cvt.rn.relu)
+template <int kFmt>
+__device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+  uint32_t r;
+  if (kFmt == 1)
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // byte offset of element (row, col) inside a [rows x 64] 16-bit K-major tile with the 128B swizzle
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t col) {
