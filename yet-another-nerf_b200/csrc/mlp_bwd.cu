@@ -1,15 +1,655 @@
-// Backward of the fused NeRF-MLP (placeholder until the tcgen05 data-/weight-gradient kernels land).
+// Backward of the fused NeRF-MLP for sm_100a (autograd of yanerf/pipelines/models/nerf_mlp.py:117-177).
+//
+// Three stages, all reading the 16-bit activation stash the forward kernel wrote:
+//   1. mlp_bwd_dgrad_kernel   fused data-gradient chain, tile-pair persistent like the forward: colour head ->
+//                             colour hidden -> intermediate -> trunk layers n-1..1.  A = dY tile in shared memory
+//                             (K-major), B = transposed weight blocks streamed by TMA, fp32 accumulate in TMEM;
+//                             the epilogue applies the ReLU mask (from the stash) and writes dY of the previous
+//                             layer back to shared memory and to the gradient stash.
+//   2. mlp_bwd_wgrad_kernel   per (layer, 128-output-feature half): dW = dY^T X over all points.  Both operands
+//                             are the stashed [128 points x 64 features] blocks used as MN-major UMMA operands
+//                             (the reduction runs over points), accumulators [128 x (256 + 64 + 16)] stay in TMEM
+//                             across tiles; one fp32 atomic flush per CTA.  Bias gradients come for free from the
+//                             constant-1 embedding channel (or a tile of ones for layers without it).
+//   3. small SIMT kernels     the N=1 / N=3 heads and the per-ray direction part of LinearWithRepeat
+//                             (models/utils.py:207-211).
 #include <cuda_runtime.h>
 
 #include "mlp_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ynb {
+
+constexpr int kBwdRing = 4;
+constexpr int kBwdThreads = 320;
+constexpr int kBSmemG = 0;                                  // [2][4][16 KB] dY tiles
+constexpr int kBSmemRing = kBSmemG + 2 * 4 * kBlkBytes;     // [4][16 KB]
+constexpr int kBSmemBar = kBSmemRing + kBwdRing * kBlkBytes;
+constexpr int kBwdSmemBytes = kBSmemBar + 256 + 1024;
+
+struct BwdParams {
+  Arch arch;
+  const float* directions;
+  const float* rgb;
+  const float* d_density;
+  const float* d_rgb;
+  const float* params;
+  const uint8_t* wpack;
+  const float* aux;
+  const uint8_t* stash;
+  uint8_t* gstash;
+  float* grads;
+  int64_t n_points;
+  int64_t R;
+  int P;
+};
+
+__device__ __forceinline__ void bwd_named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bwd_st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// packed 16-bit pair `dy` zeroed where the forward activation pair `act` is zero (ReLU mask)
+template <int kFmt>
+__device__ __forceinline__ uint32_t mask_pair(uint32_t dy, uint32_t act) {
+  if (kFmt == 1) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&act);
+    const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+    const __nv_bfloat162 m = __hne2(a, z);  // 1.0 / 0.0 per lane
+    const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&dy), m);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __half2 a = *reinterpret_cast<const __half2*>(&act);
+    const __half2 m = __hne2(a, __float2half2_rn(0.f));
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&dy), m);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+
+// epilogue of one 128-column half of a data-gradient step.
+// kMode 0: dY = acc; 1: dY = mask(acc); 2: dY = mask(acc + d_density * w_density)
+template <int kFmt, int kMode>
+__device__ __forceinline__ void dgrad_epilogue_half(uint32_t t_addr, int c_lo, const uint8_t* __restrict__ mask_row,
+                                                    uint32_t swz, float dd, const float* __restrict__ wd,
+                                                    uint32_t g_row) {
+  // prefetched mask units of this half (forward activations, 16 bit): 16 x 16 B
+  uint4 m[16];
+  if (kMode != 0) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = c_lo + u * 8;
+      m[u] = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)(c >> 6) * kBlkBytes + ((((c >> 3) & 7) ^ swz) << 4)));
+    }
+  }
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(t_addr + c_lo + cb * 32, v);
+    tmem_ld_wait();
+    const int c0 = c_lo + cb * 32;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+      if (kMode == 2) {
+        x0 = fmaf(dd, __ldg(wd + c0 + j), x0);
+        x1 = fmaf(dd, __ldg(wd + c0 + j + 1), x1);
+      }
+      pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
+    }
+    if (kMode != 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 mu = m[cb * 4 + i];
+        pk[4 * i] = mask_pair<kFmt>(pk[4 * i], mu.x);
+        pk[4 * i + 1] = mask_pair<kFmt>(pk[4 * i + 1], mu.y);
+        pk[4 * i + 2] = mask_pair<kFmt>(pk[4 * i + 2], mu.z);
+        pk[4 * i + 3] = mask_pair<kFmt>(pk[4 * i + 3], mu.w);
+      }
+    }
+    const uint32_t blk = g_row + (c0 >> 6) * kBlkBytes;
+    const uint32_t u0 = ((c0 >> 5) & 1) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      bwd_st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  }
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_g = smem_base + kBSmemG;
+  const uint32_t s_ring = smem_base + kBSmemRing;
+  const uint32_t s_bar = smem_base + kBSmemBar;
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kBwdRing, bar_hfull = s_bar + 16 * kBwdRing,
+                 bar_b01 = bar_hfull + 16, bar_epi = bar_b01 + 8, s_tmem_ptr = bar_epi + 16;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const Arch& A = p.arch;
+  const int n = A.n_layers;
+  const int n_steps = n + 1;  // layers n+1 (colour hidden), n (intermediate), n-1 .. 1
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  const int blocks_per_tile = A.stash_blocks_per_tile();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBwdRing; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_hfull, 1);
+    mbar_init(bar_hfull + 8, 1);
+    mbar_init(bar_b01, 1);
+    mbar_init(bar_epi, 256);
+    mbar_init(bar_epi + 8, 256);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s_tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: transposed weight blocks
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      const uint8_t* wsrc = p.wpack + (size_t)A.total_stages() * kBlkBytes;
+      int total = 0;
+      for (int l = n + 1; l >= 1; --l) total += A.bwd_stages(l);
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int s = 0; s < total; ++s) {
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * slot, kBlkBytes);
+          bulk_g2s(s_ring + slot * kBlkBytes, wsrc + (size_t)s * kBlkBytes, kBlkBytes, bar_full + 8 * slot);
+          if (++slot == kBwdRing) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(128, 128, kFmt, 0, 0);
+      uint32_t slot = 0, phase = 0, ed_phase0 = 0, ed_phase1 = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int st = 0; st < n_steps; ++st) {
+          const int nkb = st == 0 ? 2 : 4;  // reduction over the layer's outputs (128 for the colour hidden layer)
+          mbar_wait(bar_epi, ed_phase0);
+          ed_phase0 ^= 1;
+          tc_fence_after();
+          bool waited1 = false;
+          for (int nh = 0; nh < 2; ++nh) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (!waited1 && (nh == 1 || kb >= 2)) {
+                mbar_wait(bar_epi + 8, ed_phase1);
+                ed_phase1 ^= 1;
+                tc_fence_after();
+                waited1 = true;
+              }
+              mbar_wait(bar_full + 8 * slot, phase);
+              tc_fence_after();
+              const uint32_t b_base = s_ring + slot * kBlkBytes;
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint32_t a_base = s_g + (g * 4 + kb) * kBlkBytes;
+                const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d_tmem, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
+                           (kb | k) != 0);
+              }
+              umma_commit(bar_empty + 8 * slot);
+              if (++slot == kBwdRing) { slot = 0; phase ^= 1; }
+              if (nh == 1 && kb == 1) umma_commit(bar_b01);
+            }
+            umma_commit(bar_hfull + 8 * nh);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue groups
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
+    const uint32_t g_g = s_g + g * 4 * kBlkBytes;
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const uint32_t g_row = g_g + static_cast<uint32_t>(row) * 128u;
+    const bool leader = (warp - 2) % 4 == 0 && lane == 0;
+    const float* wd = p.aux + A.aux_wd();
+    const float* w2 = p.aux + A.aux_w2();
+    const int C = A.color_dim;
+    uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + g;
+      const bool tile_live = tile < n_tiles;
+      const int64_t gidx = tile * kTileM + row;
+      const bool valid = gidx < p.n_points;
+      // rows of partner tiles beyond the end alias tile 0 of the stash for reads; their gradients are zero
+      const int64_t rtile = tile_live ? tile : 0;
+      const uint8_t* stash_row = p.stash + (size_t)rtile * blocks_per_tile * kBlkBytes + (size_t)row * 128;
+      uint8_t* gstash_tile = p.gstash + (size_t)rtile * blocks_per_tile * kBlkBytes;
+
+      if (leader) bulk_wait_read<0>();
+      bwd_named_bar_sync(1 + g, 128);
+      // ---- head gradients: d(pre-sigmoid) -> d(colour hidden, pre-ReLU) = mask(hid) * (W2^T ds)
+      float ds[4] = {0.f, 0.f, 0.f, 0.f};
+      float dd = 0.f;
+      if (valid) {
+        dd = __ldg(p.d_density + gidx);
+        for (int c = 0; c < C; ++c) {
+          const float y = __ldg(p.rgb + gidx * C + c);
+          ds[c] = __ldg(p.d_rgb + gidx * C + c) * y * (1.f - y);
+        }
+      }
+      {
+        const uint8_t* hid_row = stash_row + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
+#pragma unroll 1
+        for (int u = 0; u < 16; ++u) {  // 16 units of 8 columns = 128 hidden features
+          const int c0 = u * 8;
+          const uint4 hu = __ldg(reinterpret_cast<const uint4*>(hid_row + (size_t)(c0 >> 6) * kBlkBytes + ((((c0 >> 3) & 7) ^ swz) << 4)));
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = 0.f;
+          for (int c = 0; c < C; ++c) {
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0));
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0 + 4));
+            x[0] = fmaf(ds[c], wa.x, x[0]); x[1] = fmaf(ds[c], wa.y, x[1]);
+            x[2] = fmaf(ds[c], wa.z, x[2]); x[3] = fmaf(ds[c], wa.w, x[3]);
+            x[4] = fmaf(ds[c], wb.x, x[4]); x[5] = fmaf(ds[c], wb.y, x[5]);
+            x[6] = fmaf(ds[c], wb.z, x[6]); x[7] = fmaf(ds[c], wb.w, x[7]);
+          }
+          const uint32_t p0 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[0], x[1]), hu.x);
+          const uint32_t p1 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[2], x[3]), hu.y);
+          const uint32_t p2 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[4], x[5]), hu.z);
+          const uint32_t p3 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[6], x[7]), hu.w);
+          bwd_st_shared_v4(g_row + (c0 >> 6) * kBlkBytes + ((((c0 >> 3) & 7) ^ swz) << 4), p0, p1, p2, p3);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(bar_epi);
+      mbar_arrive(bar_epi + 8);
+      bwd_named_bar_sync(1 + g, 128);
+      if (leader && tile_live) {
+        uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
+        bulk_s2g(dst, g_g, kBlkBytes);
+        bulk_s2g(dst + kBlkBytes, g_g + kBlkBytes, kBlkBytes);
+        bulk_commit();
+      }
+
+      for (int st = 0; st < n_steps; ++st) {
+        const int l = n + 1 - st;                 // layer whose data gradient was just multiplied
+        const int prev = l - 1;                   // mma layer whose output gradient this epilogue produces
+        const bool last = st == n_steps - 1;
+        const uint8_t* mask_row = stash_row + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
+        // ---- half 0
+        mbar_wait(bar_hfull, hf_phase0);
+        hf_phase0 ^= 1;
+        mbar_wait(bar_b01, b01_phase);
+        b01_phase ^= 1;
+        tc_fence_after();
+        if (leader) bulk_wait_read<0>();
+        bwd_named_bar_sync(1 + g, 128);
+        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mask_row, swz, dd, wd, g_row);
+        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mask_row, swz, dd, wd, g_row);
+        else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mask_row, swz, dd, wd, g_row);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        if (!last) mbar_arrive(bar_epi);
+        // ---- half 1
+        mbar_wait(bar_hfull + 8, hf_phase1);
+        hf_phase1 ^= 1;
+        tc_fence_after();
+        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mask_row, swz, dd, wd, g_row);
+        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mask_row, swz, dd, wd, g_row);
+        else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mask_row, swz, dd, wd, g_row);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        if (!last) mbar_arrive(bar_epi + 8);
+        bwd_named_bar_sync(1 + g, 128);
+        if (leader && tile_live) {
+          uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
+          for (int b = 0; b < 4; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, g_g + b * kBlkBytes, kBlkBytes);
+          bulk_commit();
+        }
+      }
+    }
+    if (leader) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 192;
+constexpr int kWgStageBytes = 7 * kBlkBytes;  // 2 dY blocks + 4 hidden blocks + 1 embedding block
+constexpr int kWgStages = 2;
+constexpr int kWgSmemOnes = kWgStages * kWgStageBytes;  // 1 KB of ones
+constexpr int kWgSmemBar = kWgSmemOnes + 1024;
+constexpr int kWgSmemBytes = kWgSmemBar + 128 + 1024;
+
+// MN-major operand over [points x 64-feature blocks]: atoms of 64 features (128 B) x 8 points, 8-point groups 1024 B
+// apart (SBO), 64-feature blocks 16 KB apart (LBO)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr) { return umma_desc_sw128(smem_addr, kBlkBytes, 1024); }
+
+template <int kFmt>
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdParams p, int n_jobs, int n_splits) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_ones = smem_base + kWgSmemOnes;
+  const uint32_t s_bar = smem_base + kWgSmemBar;
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 16, bar_done = s_bar + 32, s_tmem_ptr = s_bar + 40;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const Arch& A = p.arch;
+  const int n = A.n_layers;
+  const int job = blockIdx.x % n_jobs;
+  const int split = blockIdx.x / n_jobs;
+  // job -> (layer, output half); the colour hidden layer has a single half
+  const int l = job < 2 * (n + 1) ? job / 2 : n + 1;
+  const int mh = job < 2 * (n + 1) ? job % 2 : 0;
+  const bool has_hidden = l >= 1;
+  const bool has_emb = A.has_emb(l);
+  const bool use_ones = !has_emb;  // bias gradient via a tile of ones when there is no constant-1 channel
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int blocks_per_tile = A.stash_blocks_per_tile();
+  // X_l: output of the previous mma layer (the colour hidden layer reads the intermediate output)
+  const int xprev = l - 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_done, 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {  // 1 KB of 16-bit ones
+    const uint32_t one2 = Half2Pack<kFmt>::pack(1.f, 1.f);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(s_ones + 4 * i), "r"(one2) : "memory");
+  }
+  fence_proxy_async_smem();
+  if (warp == 1) {
+    tmem_alloc(s_tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
+
+  const uint32_t stage_bytes = (2 + (has_hidden ? 4 : 0) + (has_emb ? 1 : 0)) * kBlkBytes;
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      for (int64_t t = split; t < n_tiles; t += n_splits) {
+        const uint8_t* st = p.stash + (size_t)t * blocks_per_tile * kBlkBytes;
+        const uint8_t* gs = p.gstash + (size_t)t * blocks_per_tile * kBlkBytes;
+        const uint32_t dst = smem_base + slot * kWgStageBytes;
+        const uint32_t bar = bar_full + 8 * slot;
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        mbar_arrive_expect_tx(bar, stage_bytes);
+        bulk_g2s(dst, gs + (size_t)(A.stash_block_of_layer(l) + 2 * mh) * kBlkBytes, 2 * kBlkBytes, bar);
+        if (has_hidden) bulk_g2s(dst + 2 * kBlkBytes, st + (size_t)A.stash_block_of_layer(xprev) * kBlkBytes, 4 * kBlkBytes, bar);
+        if (has_emb) bulk_g2s(dst + 6 * kBlkBytes, st, kBlkBytes, bar);
+        if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc256 = umma_idesc(128, 256, kFmt, 1, 1);
+      constexpr uint32_t idesc64 = umma_idesc(128, 64, kFmt, 1, 1);
+      constexpr uint32_t idesc16 = umma_idesc(128, 16, kFmt, 1, 1);
+      uint32_t slot = 0, phase = 0;
+      uint32_t first = 1;
+      const uint64_t ones_desc = umma_desc_sw128(s_ones, 128, 256) & ~(static_cast<uint64_t>(7) << 61);  // no swizzle
+      for (int64_t t = split; t < n_tiles; t += n_splits) {
+        const uint32_t base = smem_base + slot * kWgStageBytes;
+        mbar_wait(bar_full + 8 * slot, phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 16 points per MMA
+          const uint64_t a_desc = umma_desc_mnmajor(base + k * 2048);
+          const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          if (has_hidden) umma_f16(tmem_base, a_desc, umma_desc_mnmajor(base + 2 * kBlkBytes + k * 2048), idesc256, acc);
+          if (has_emb) umma_f16(tmem_base + 256, a_desc, umma_desc_mnmajor(base + 6 * kBlkBytes + k * 2048), idesc64, acc);
+          if (use_ones) umma_f16(tmem_base + 320, a_desc, ones_desc, idesc16, acc);
+        }
+        first = 0;
+        umma_commit(bar_empty + 8 * slot);
+        if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+      }
+      umma_commit(bar_done);
+    }
+    __syncwarp();
+  } else if (split < n_tiles) {
+    // ---------------------------------------------------------------- flush: TMEM -> fp32 atomics
+    const int q = warp & 3;
+    const int out = mh * 128 + q * 32 + lane;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int dout = A.dout(l), din = A.din(l), hin = A.hidden_in(l), exyz = A.embed_xyz();
+    float* W = p.grads + A.w_offset(l) + (int64_t)out * din;
+    float* bgrad = p.grads + A.b_offset(l) + out;
+    const bool row_ok = out < dout;
+    if (has_hidden) {
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(t_row + cb * 32, v);
+        tmem_ld_wait();
+        if (row_ok)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cb * 32 + j < hin) atomicAdd(W + cb * 32 + j, __uint_as_float(v[j]));
+      }
+    }
+    if (has_emb) {
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(t_row + 256 + cb * 32, v);
+        tmem_ld_wait();
+        if (row_ok)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int e = cb * 32 + j;
+            if (e < exyz) atomicAdd(W + hin + e, __uint_as_float(v[j]));
+            else if (e == 63) atomicAdd(bgrad, __uint_as_float(v[j]));  // constant-1 channel -> bias
+          }
+      }
+    }
+    if (use_ones) {
+      uint32_t v[32];
+      tmem_ld32(t_row + 320, v);  // columns 320..335 hold 16 identical sums (the rest is unused)
+      tmem_ld_wait();
+      if (row_ok) atomicAdd(bgrad, __uint_as_float(v[0]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small heads: density layer (N = 1), colour output layer (N = color_dim)
+// ------------------------------------------------------------------------------------------------
+template <int kFmt>
+__device__ __forceinline__ float half_at(const uint8_t* tile_layer, int row, int col) {
+  const uint16_t bits = *reinterpret_cast<const uint16_t*>(tile_layer + (size_t)(col >> 6) * kBlkBytes + sw128_offset(row, col & 63));
+  if (kFmt == 1) return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits));
+  return __half2float(*reinterpret_cast<const __half*>(&bits));
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
+  __shared__ float s_dd[kTileM];
+  __shared__ float s_ds[kTileM][4];
+  const Arch& A = p.arch;
+  const int n = A.n_layers, C = A.color_dim;
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int blocks_per_tile = A.stash_blocks_per_tile();
+  const int j = threadIdx.x;  // feature column
+  float acc_wd = 0.f, acc_w2[4] = {0.f, 0.f, 0.f, 0.f}, acc_bd = 0.f, acc_b2 = 0.f;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __syncthreads();
+    if (j < kTileM) {
+      const int64_t gidx = t * kTileM + j;
+      float dd = 0.f, ds[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gidx < p.n_points) {
+        dd = p.d_density[gidx];
+        for (int c = 0; c < C; ++c) {
+          const float y = p.rgb[gidx * C + c];
+          ds[c] = p.d_rgb[gidx * C + c] * y * (1.f - y);
+        }
+      }
+      s_dd[j] = dd;
+      for (int c = 0; c < 4; ++c) s_ds[j][c] = ds[c];
+    }
+    __syncthreads();
+    const uint8_t* tile = p.stash + (size_t)t * blocks_per_tile * kBlkBytes;
+    const uint8_t* feat = tile + (size_t)A.stash_block_of_layer(n - 1) * kBlkBytes;  // last trunk output
+    const uint8_t* hid = tile + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;   // colour hidden
+    for (int r = 0; r < kTileM; ++r) {
+      acc_wd = fmaf(s_dd[r], half_at<kFmt>(feat, r, j), acc_wd);
+      if (j < kDirPad) {
+        const float h = half_at<kFmt>(hid, r, j);
+        for (int c = 0; c < C; ++c) acc_w2[c] = fmaf(s_ds[r][c], h, acc_w2[c]);
+      }
+    }
+    if (j == 0)
+      for (int r = 0; r < kTileM; ++r) acc_bd += s_dd[r];
+    if (j >= 1 && j <= C)
+      for (int r = 0; r < kTileM; ++r) acc_b2 += s_ds[r][j - 1];
+  }
+  if (j < A.hidden_last) atomicAdd(p.grads + A.density_w_offset() + j, acc_wd);
+  if (j == 0) atomicAdd(p.grads + A.density_b_offset(), acc_bd);
+  if (j < A.hidden_dir)
+    for (int c = 0; c < C; ++c) atomicAdd(p.grads + A.color2_w_offset() + (int64_t)c * A.hidden_dir + j, acc_w2[c]);
+  if (j >= 1 && j <= C) atomicAdd(p.grads + A.color2_b_offset() + j - 1, acc_b2);
+}
+
+// per-ray direction part of the colour hidden layer: dW_c[:, H + k] += sum_rays (sum_samples dY[ray, s, :]) emb27[ray][k]
+// one warp per ray; lane owns 4 of the 128 hidden columns
+template <int kFmt>
+__global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
+  __shared__ float s_acc[kDirPad * 28];  // [j][k], 27 direction-embedding channels (+pad)
+  const Arch& A = p.arch;
+  const int n = A.n_layers;
+  const int ed = A.embed_dir();
+  const int blocks_per_tile = A.stash_blocks_per_tile();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < kDirPad * 28; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const size_t layer_off = (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
+  for (int64_t ray = (int64_t)blockIdx.x * nw + wib; ray < p.R; ray += (int64_t)gridDim.x * nw) {
+    float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.P; ++s) {
+      const int64_t gidx = ray * p.P + s;
+      const int64_t t = gidx / kTileM;
+      const int r = (int)(gidx % kTileM);
+      const uint8_t* tile = p.gstash + (size_t)t * blocks_per_tile * kBlkBytes + layer_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gsum[i] += half_at<kFmt>(tile, r, lane * 4 + i);
+    }
+    // direction embedding of this ray (same arithmetic as dirbias_kernel)
+    const float dx = p.directions[ray * 3], dy = p.directions[ray * 3 + 1], dz = p.directions[ray * 3 + 2];
+    const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+    const float d[3] = {dx / nrm, dy / nrm, dz / nrm};
+    const int nf = A.n_freq_dir;
+    for (int k = 0; k < ed; ++k) {
+      float e;
+      if (k < 3 * nf) e = sinf(d[k / nf] * exp2f((float)(k % nf)));
+      else if (k < 6 * nf) e = cosf(d[(k - 3 * nf) / nf] * exp2f((float)((k - 3 * nf) % nf)));
+      else e = d[k - 6 * nf];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[(lane * 4 + i) * 28 + k], gsum[i] * e);
+    }
+  }
+  __syncthreads();
+  const int din = A.din(n + 1);
+  float* W = p.grads + A.w_offset(n + 1);
+  for (int i = threadIdx.x; i < A.hidden_dir * ed; i += blockDim.x) {
+    const int j = i / ed, k = i % ed;
+    atomicAdd(W + (int64_t)j * din + A.hidden_last + k, s_acc[j * 28 + k]);
+  }
+}
+
+static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
+  const Arch& A = p.arch;
+  const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(n_pairs < sms ? n_pairs : sms);
+  const int n_jobs = 2 * (A.n_layers + 1) + 1;
+  int n_splits = sms / n_jobs;
+  if (n_splits < 1) n_splits = 1;
+  if (n_splits > n_tiles) n_splits = (int)n_tiles;
+  auto run = [&](auto dgrad, auto wgrad, auto heads, auto dir) {
+    cudaFuncSetAttribute(dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+    cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+    dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
+    wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
+    heads<<<(int)(n_tiles < 2 * sms ? n_tiles : 2 * sms), 256, 0, stream>>>(p);
+    const int64_t ray_blocks = (p.R + 7) / 8;
+    dir<<<(int)(ray_blocks < sms ? ray_blocks : sms), 256, 0, stream>>>(p);
+  };
+  if (A.fmt == 1)
+    run(mlp_bwd_dgrad_kernel<1>, mlp_bwd_wgrad_kernel<1>, mlp_bwd_heads_kernel<1>, mlp_bwd_dir_kernel<1>);
+  else
+    run(mlp_bwd_dgrad_kernel<0>, mlp_bwd_wgrad_kernel<0>, mlp_bwd_heads_kernel<0>, mlp_bwd_dir_kernel<0>);
+  return check_launch("yn_mlp_bwd");
+}
+
+}  // namespace ynb
 
 extern "C" int64_t yn_mlp_bwd_workspace_bytes(const yn_mlp_arch* arch, int64_t n_points) {
-  if (ynb::check_arch(arch) || n_points < 0) return -1;
-  return 256;
+  // the gradient stash mirrors the activation stash (one 16-bit dY image per layer and tile)
+  return yn_mlp_stash_bytes(arch, n_points);
 }
 
 extern "C" int yn_mlp_bwd(const yn_mlp_arch* arch, const float* directions, const float* rgb, const float* d_density,
                           const float* d_rgb, const float* params, const void* wpack, const float* aux,
                           const void* stash, void* workspace, float* grads, int64_t R, int P, void* stream) {
-  return ynb::fail(YN_ERR_UNSUPPORTED, "yn_mlp_bwd: not implemented yet");
+  if (int rc = ynb::check_arch(arch)) return rc;
+  if (R < 0 || P <= 0) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_bwd: bad sizes R=%lld P=%d", (long long)R, P);
+  if (R == 0) return YN_OK;
+  if (!directions || !rgb || !d_density || !d_rgb || !params || !wpack || !aux || !stash || !workspace || !grads)
+    return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_bwd: null pointer");
+  ynb::BwdParams p;
+  p.arch = ynb::arch_from_c(arch);
+  p.directions = directions;
+  p.rgb = rgb;
+  p.d_density = d_density;
+  p.d_rgb = d_rgb;
+  p.params = params;
+  p.wpack = static_cast<const uint8_t*>(wpack);
+  p.aux = aux;
+  p.stash = static_cast<const uint8_t*>(stash);
+  p.gstash = static_cast<uint8_t*>(workspace);
+  p.grads = grads;
+  p.n_points = R * P;
+  p.R = R;
+  p.P = P;
+  return ynb::launch_bwd(p, static_cast<cudaStream_t>(stream));
 }

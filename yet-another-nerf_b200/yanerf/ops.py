@@ -155,9 +155,9 @@ class MlpFunction(torch.autograd.Function):
     (the reference never differentiates w.r.t. the rays); the flat parameter vector does."""
 
     @staticmethod
-    def forward(ctx, flat_params, origins, directions, lengths, plan: MlpPlan):
+    def forward(ctx, flat_params, origins, directions, lengths, plan: MlpPlan, need_grad: bool):
+        # NB: grad mode is off inside Function.forward, so the caller decides whether to keep the stash
         R, P = lengths.shape
-        need_grad = flat_params.requires_grad and torch.is_grad_enabled()
         stash = None
         if need_grad and R > 0:
             nbytes = N.lib().yn_mlp_stash_bytes(ctypes.byref(plan.arch), R * P)
@@ -187,7 +187,7 @@ class MlpFunction(torch.autograd.Function):
                     N.ptr(work, torch.uint8), N.ptr(grads), R, P, N.stream_ptr(),
                 )
         ctx.stash = None
-        return grads, None, None, None, None
+        return grads, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------- #

@@ -51,8 +51,15 @@ class MLPWithInputSkips(torch.nn.Module):
         self._input_skips = set(input_skips)
 
 
-def _default_fmt() -> int:
-    return {"fp16": N.FMT_FP16, "bf16": N.FMT_BF16}[os.environ.get("YANERF_MLP_DTYPE", "fp16").lower()]
+_FMT = {"fp16": N.FMT_FP16, "bf16": N.FMT_BF16}
+
+
+def _default_fmt(training: bool) -> int:
+    """Tensor-core operand type.  Inference: fp16 (10-bit mantissa, 4x tighter than bf16; NeRF activations are far
+    inside its range).  Training: bf16 for activations AND gradients (no loss scaling needed)."""
+    if training:
+        return _FMT[os.environ.get("YANERF_MLP_TRAIN_DTYPE", "bf16").lower()]
+    return _FMT[os.environ.get("YANERF_MLP_DTYPE", "fp16").lower()]
 
 
 @MODELS.register_module()
@@ -122,10 +129,10 @@ class NeRFMLP(torch.nn.Module):
         for li in self.input_skips:
             if 0 < li < n_layers:
                 skip_mask |= 1 << li
-        self._arch = N.MlpArch(n_layers, skip_mask, n_harmonic_functions_xyz, n_harmonic_functions_dir,
-                               n_hidden_neurons_xyz, n_hidden_neurons_dir, color_dim, _default_fmt())
-        self._plan: Optional[ops.MlpPlan] = None
-        self._packed_key = None
+        self._arch_fields = (n_layers, skip_mask, n_harmonic_functions_xyz, n_harmonic_functions_dir,
+                             n_hidden_neurons_xyz, n_hidden_neurons_dir, color_dim)
+        self._fmt = {False: _default_fmt(False), True: _default_fmt(True)}  # keyed by "needs grad"
+        self._plans = {}  # fmt -> [MlpPlan, packed key]
 
     # ------------------------------------------------------------------ parameter plumbing
     def ordered_parameters(self) -> List[torch.nn.Parameter]:
@@ -138,25 +145,33 @@ class NeRFMLP(torch.nn.Module):
         ps += [self.color_layer[0].weight, self.color_layer[0].bias, self.color_layer[2].weight, self.color_layer[2].bias]
         return ps
 
-    def set_operand_dtype(self, name: str) -> None:
-        """'bf16' or 'fp16' tensor-core operands (fp32 accumulation either way)."""
-        self._arch.fmt = {"fp16": N.FMT_FP16, "bf16": N.FMT_BF16}[name]
-        self._packed_key = None
+    def set_operand_dtype(self, name: str, training: Optional[bool] = None) -> None:
+        """'bf16' or 'fp16' tensor-core operands (fp32 accumulation either way) for inference, training or
+        (training=None) both."""
+        for mode in ((False, True) if training is None else (training,)):
+            self._fmt[mode] = _FMT[name]
 
     def _flat(self) -> torch.Tensor:
         return torch.cat([p.reshape(-1) for p in self.ordered_parameters()])
 
-    def plan_for(self, flat: torch.Tensor) -> ops.MlpPlan:
+    def plan_for(self, flat: torch.Tensor, needs_grad: bool) -> ops.MlpPlan:
         """(Re)pack the tensor-core weight image when the parameters changed since the last call."""
+        fmt = self._fmt[bool(needs_grad)]
         ps = self.ordered_parameters()
-        key = (self._arch.fmt, str(flat.device)) + tuple((p.data_ptr(), p._version) for p in ps)
-        if self._plan is None or self._plan.wpack.device != flat.device:
-            self._plan = ops.MlpPlan.create(self._arch, flat.device)
-            self._packed_key = None
-        if key != self._packed_key:
-            self._plan.pack(flat.detach())
-            self._packed_key = key
-        return self._plan
+        key = (str(flat.device),) + tuple((p.data_ptr(), p._version) for p in ps)
+        entry = self._plans.get(fmt)
+        if entry is None or entry[0].wpack.device != flat.device:
+            entry = [ops.MlpPlan.create(N.MlpArch(*self._arch_fields, fmt), flat.device), None]
+            self._plans[fmt] = entry
+        if key != entry[1]:
+            entry[0].pack(flat.detach())
+            entry[1] = key
+        return entry[0]
+
+    def invalidate_packed_weights(self) -> None:
+        """Call after updating parameters behind torch's back (e.g. a fused optimizer kernel)."""
+        for entry in self._plans.values():
+            entry[1] = None
 
     # ------------------------------------------------------------------ forward
     def forward(self, origins: torch.Tensor, directions: torch.Tensor, lengths: torch.Tensor,
@@ -168,11 +183,12 @@ class NeRFMLP(torch.nn.Module):
         lead = lengths.shape[:-1]
         P = lengths.shape[-1]
         flat = self._flat()
-        plan = self.plan_for(flat)
+        need_grad = torch.is_grad_enabled() and flat.requires_grad
+        plan = self.plan_for(flat, need_grad)
         o = N.f32c(origins.expand(*lead, 3)).reshape(-1, 3)
         d = N.f32c(directions.expand(*lead, 3)).reshape(-1, 3)
         z = N.f32c(lengths).reshape(-1, P)
-        density, rgb = ops.MlpFunction.apply(flat, o, d, z, plan)
+        density, rgb = ops.MlpFunction.apply(flat, o, d, z, plan, need_grad)
         return dict(
             rays_densities=density.reshape(*lead, P, 1),
             rays_features=rgb.reshape(*lead, P, self.color_dim),
