@@ -155,3 +155,92 @@ def test_renderer_two_pass_same_model_runs():
         assert out.aux["weights"].shape == (3, 4, 5, n) and out.prev_stage.aux["weights"].shape == (3, 4, 5, 6)
     with pytest.raises(ValueError, match="expects implicit functions"):
         ren(o, d, z, xy, bg, implicit_functions=[])
+
+
+# --------------------------------------------------------------------------- training step
+import contextlib
+
+
+@contextlib.contextmanager
+def inject_draws(multinomial, rand, randn_like):
+    """Replay pre-generated draws into torch.multinomial / torch.rand / torch.randn_like in call order (the
+    pipeline draws: pixels, stratified jitter, coarse noise, sample_pdf uniforms, fine noise)."""
+    q = {"multinomial": list(multinomial), "rand": list(rand), "randn_like": list(randn_like)}
+    saved = {k: getattr(torch, k) for k in q}
+
+    def mk(name):
+        def f(*a, **kw):
+            return q[name].pop(0).clone()
+        return f
+
+    for k in q:
+        setattr(torch, k, mk(k))
+    try:
+        yield
+    finally:
+        for k, v in saved.items():
+            setattr(torch, k, v)
+    for k, v in q.items():
+        assert not v, f"unused injected draws for {k}"
+
+
+@pytest.mark.parametrize("tag,n_fine,std,gain", [("fern", 64, 0.0, 1.0), ("lego", 128, 0.2, 3.0)])
+def test_train_forward_backward_vs_reference_golden(golden, tag, n_fine, std, gain):
+    """TRAINING forward with the reference's draws replayed: losses vs the unmodified reference (golden), then
+    backward: gradient summaries vs the reference's autograd."""
+    g = golden("pipeline")
+    B, H, W, n = 2, 16, 20, 48
+    pipe = build_pipeline(H, W, n, n_fine, std, chunk=64 * 37).to(DEV)
+    load_synth_nets(pipe, seeds=(21, 22), gain=gain)
+    poses, focal, image = syn.synth_camera(B, seed=5), torch.full((B, 1), 25.0), syn.synth_image(B, H, W, seed=4)
+    dr = {k: v.to(DEV) for k, v in syn.synth_draws(B, n, H * W, 64, n_fine, seed=6).items()}
+    randn = [dr["noise0"], dr["noise1"]] if std > 0 else []
+    with inject_draws([dr["pix"]], [dr["u_strat"], dr["u_pdf"]], randn):
+        preds = pipe(poses=poses.to(DEV), focal_lengths=focal.to(DEV), image_rgb=image.to(DEV),
+                     evaluation_mode=EvaluationMode.TRAINING)
+    assert preds["objective"].shape == (B,)
+    assert preds["rendered_images"].shape == (B, H, W, 3)
+    tol = 2e-3 if gain == 1.0 else 5e-2
+    for k in ("loss_rgb_mse", "loss_prev_stage_rgb_mse", "loss_rgb_huber", "objective"):
+        got, ref = preds[k].detach().cpu(), T(g[f"{tag}_train_{k}"])
+        print(tag, k, got.tolist(), ref.tolist())
+        assert float((got - ref).abs().max()) <= tol, (k, got, ref)
+    if gain == 1.0:
+        err = float((preds["rendered_images"].cpu() - T(g[f"{tag}_train_rendered_images"])).abs().max())
+        assert err <= 4e-3, err  # bf16 operands in training
+    preds["objective"].mean().backward()
+    for k, fn in enumerate(pipe.implicit_functions):
+        for name, p in fn._fn.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        gw = fn._fn.density_layer.weight.grad.cpu()
+        ref = T(g[f"{tag}_grad{k}_full_density_w"])
+        cos = float((gw * ref).sum() / (gw.norm() * ref.norm()).clamp_min(1e-30))
+        print(tag, k, "density_w grad cos", cos, float(gw.norm()), float(ref.norm()))
+        if gain == 1.0:
+            assert cos >= 0.98, cos
+            assert abs(float(gw.norm()) / float(ref.norm()) - 1) <= 0.1
+
+
+def test_fused_trainer_converges_like_reference_runner():
+    """Reference tests/test_runner.py:42-104: 2x2 image, 5+5 samples, Adam iterations -> objective < 0.01."""
+    from yanerf.pipelines import PIPELINES
+    from yanerf.runners import FusedTrainer
+
+    torch.manual_seed(0)
+    cfg = pipeline_cfg(2, 2, 4, 5, 0.0, chunk=0, min_depth=0.1, max_depth=2.0)
+    cfg.ray_sampler.n_pts_per_ray_training = 5
+    cfg.ray_sampler.n_pts_per_ray_evaluation = 5
+    pipe = PIPELINES.build(cfg).to(DEV)
+    trainer = FusedTrainer(pipe, lr=5e-3)
+    batch = dict(poses=syn.synth_camera(1, seed=0).to(DEV), focal_lengths=torch.full((1, 1), 2.0, device=DEV),
+                 image_rgb=torch.rand(1, 2, 2, 3, device=DEV))
+    first = None
+    for it in range(200):
+        preds = trainer.train_step(batch)
+        if first is None:
+            first = float(preds["objective"].mean())
+    with torch.no_grad():
+        ev = pipe(**batch, evaluation_mode=EvaluationMode.EVALUATION)
+    last = float(ev["objective"].mean())
+    print("objective", first, "->", last)
+    assert last < 0.01 and last < first

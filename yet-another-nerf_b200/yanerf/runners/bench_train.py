@@ -1,0 +1,97 @@
+"""`bench.py --workload train`: the lego.yml training step (BASELINE.json configs[2]): 4096 rays per GPU,
+64 coarse + 192 fine points per ray, two 8x256 MLPs forward + backward, Adam, gradient all-reduce for N > 1."""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def run_train_bench(args, rank: int, world: int, dev) -> None:
+    import bench as B
+    from yanerf import ops
+    from yanerf.runners.engine import FusedTrainer
+
+    n_rays = 4096
+    peaks = B.load_peaks()
+    pipe, _ = B.build_lego_pipeline(dev, n_rays=n_rays)
+    trainer = FusedTrainer(pipe, lr=5e-4 * world)  # linear LR scaling, scripts/run.py:152-156
+    poses, focal, image = B.synthetic_inputs(rank)
+    batch_d = dict(poses=poses.to(dev), focal_lengths=focal.to(dev), image_rgb=image.to(dev))
+    host = dict(poses=poses.pin_memory(), focal_lengths=focal.pin_memory(), image_rgb=image.pin_memory())
+    loss_h = torch.empty(1).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host.values())
+
+    def step_resident():
+        return trainer.train_step(batch_d)
+
+    def step_e2e():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        preds = trainer.train_step(b)
+        loss_h.copy_(preds["objective"], non_blocking=True)
+        return preds
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler = B.ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    ops.Profiler.reset()
+    ops.Profiler.enabled = True
+    l0 = ops.Profiler.launches
+    total_ms = timed(step_resident, args.steps)
+    ops.Profiler.enabled = False
+    launches = (ops.Profiler.launches - l0) // max(1, args.steps)
+    prof = ops.Profiler.summary()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    rays = n_rays * world
+    value = rays * args.steps / (total_ms * 1e-3)
+    e2e_value = rays * args.steps / (e2e_ms * 1e-3)
+    mlp_ms = sum(prof.get(k, (0, 0.0))[1] for k in ("yn_mlp_fwd", "yn_mlp_bwd")) / args.steps
+    flops = n_rays * (B.N_COARSE + B.N_COARSE + B.N_FINE) * B.FLOP_PER_POINT_TRAIN
+    achieved = flops / (mlp_ms * 1e-3) / 1e12
+    if rank == 0:
+        line = dict(
+            metric="train rays/sec (lego.yml step, 4096 rays/GPU, 64+192 points/ray)", value=round(value, 1), unit="rays/s",
+            n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=round(total_ms / args.steps, 3),
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 operands, f32 accumulate / master weights",
+            data="synthetic",
+            config={"workload": "lego.yml training step, 4096 rays/GPU, coarse+fine fwd/bwd + Adam, ray-sharded DDP",
+                    "l2": "stash + gradient stash of one step (~10 GB) exceed the 126 MB L2", "parallelism": f"dp{world}"},
+            clocks=clocks, gpu_launches=int(launches),
+            e2e={"value": round(e2e_value, 1), "unit": "rays/s", "ms_per_step": round(e2e_ms / args.steps, 3),
+                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            roofline={"bound": "tensor", "kernel": "mlp fwd + dgrad + wgrad kernels (coarse + fine)", "achieved": round(achieved, 1),
+                      "peak": peaks["tensor"], "peak_source": f"{peaks['source']} bf16_tflops_sustained", "unit": "TFLOP/s",
+                      "frac": round(achieved / peaks["tensor"], 4), "traffic": None,
+                      "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in prof.items()}},
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()

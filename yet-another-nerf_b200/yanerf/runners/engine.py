@@ -1,0 +1,102 @@
+"""Training step engine: the device side of `runners/apis.py:train_one_epoch` (53-118) for one iteration.
+
+`scripts/run.py` builds `torch.optim.Adam` over 48 tensors and wraps the pipeline in DDP (run.py:152-166); here the
+same arithmetic runs on flat buffers:
+  * every parameter (and its .grad) is a view into ONE contiguous fp32 buffer;
+  * the DDP gradient all-reduce (mean) is a single NCCL all-reduce of that flat gradient buffer;
+  * Adam is one `yn_adam_step` launch over the flat buffers (the 1/world_size of the mean folded in as grad_scale).
+The forward/backward itself is `NeRFPipeline.forward` + autograd, i.e. the kernels of ops.py.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from yanerf import ops
+from yanerf.pipelines.utils import EvaluationMode
+
+
+def exponential_lr(it: int, lr: float, min_lr: float, num_iters: int, warmup_iters: int = 0, warmup_lr: float = 0.0) -> float:
+    """Learning-rate schedule of the reference runner (runners/utils.py:65-109): linear warm-up from
+    `warmup_lr`, then exponential decay lr -> min_lr over `num_iters`."""
+    if warmup_iters > 0 and it < warmup_iters:
+        return warmup_lr + (lr - warmup_lr) * it / warmup_iters
+    t = min(max(it, 0), num_iters) / max(num_iters, 1)
+    return lr * (min_lr / lr) ** t
+
+
+class FusedTrainer:
+    """Owns flat parameter / gradient / Adam-moment buffers of a pipeline and performs one optimisation step."""
+
+    def __init__(self, pipeline: torch.nn.Module, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group: Optional[Any] = None) -> None:
+        self.pipeline = pipeline
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.params: List[torch.nn.Parameter] = [p for p in pipeline.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("pipeline has no trainable parameters")
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat[off:off + k].view_as(p)
+                p.grad = self.flat_grad[off:off + k].view_as(p)
+                off += k
+        self.step_count = 0
+        self._mlps = [m for m in pipeline.modules() if hasattr(m, "invalidate_packed_weights")]
+        self._broadcast_parameters()
+
+    def _broadcast_parameters(self) -> None:
+        if self.world > 1:
+            dist.broadcast(self.flat, src=0, group=self.group)
+            self._invalidate()
+
+    def _invalidate(self) -> None:
+        for m in self._mlps:
+            m.invalidate_packed_weights()
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+
+    def train_step(self, batch: Dict[str, Any], lr: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """forward (TRAINING) -> objective.mean().backward() -> all-reduce -> Adam.  Returns the preds dict."""
+        self.zero_grad()
+        preds = self.pipeline(**batch, evaluation_mode=EvaluationMode.TRAINING)
+        if "objective" not in preds:
+            raise KeyError("objective")  # runners/apis.py:90-91
+        preds["objective"].mean().backward()
+        self.optimizer_step(lr)
+        return preds
+
+    def optimizer_step(self, lr: Optional[float] = None) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.step_count += 1
+        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr if lr is None else lr,
+                      self.step_count, self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / self.world)
+        self._invalidate()
+
+    # checkpoint format of scripts/run.py:416-422 (model state_dict + optimizer state + epoch)
+    def state_dict(self) -> Dict[str, Any]:
+        return {"model": self.pipeline.state_dict(), "optimizer": {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                                                                    "step": self.step_count}}
+
+    def load_state_dict(self, state: Dict[str, Any]) -> None:
+        self.pipeline.load_state_dict(state["model"])
+        opt = state.get("optimizer")
+        if opt:
+            self.exp_avg.copy_(opt["exp_avg"])
+            self.exp_avg_sq.copy_(opt["exp_avg_sq"])
+            self.step_count = int(opt["step"])
+        self._invalidate()
