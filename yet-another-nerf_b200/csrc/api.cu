@@ -32,8 +32,8 @@ int check_arch(const yn_mlp_arch* a) {
   if (a->n_freq_xyz < 0 || 3 * (2 * a->n_freq_xyz + 1) > 64)
     return fail(YN_ERR_UNSUPPORTED, "xyz embedding of %d channels does not fit one 64-wide K block",
                 3 * (2 * a->n_freq_xyz + 1));
-  if (a->n_freq_dir < 0 || 3 * (2 * a->n_freq_dir + 1) > 64)
-    return fail(YN_ERR_UNSUPPORTED, "direction embedding wider than 64 channels");
+  if (a->n_freq_dir < 0 || 3 * (2 * a->n_freq_dir + 1) > 32)
+    return fail(YN_ERR_UNSUPPORTED, "direction embedding wider than 32 channels (n_harmonic_functions_dir > 4)");
   if (a->hidden_last < 1 || a->hidden_last > kInner) return fail(YN_ERR_UNSUPPORTED, "n_hidden_neurons_xyz must be in [1,256]");
   if (a->hidden_dir < 1 || a->hidden_dir > kDirPad) return fail(YN_ERR_UNSUPPORTED, "n_hidden_neurons_dir must be in [1,128]");
   if (a->color_dim < 1 || a->color_dim > 4) return fail(YN_ERR_UNSUPPORTED, "color_dim must be in [1,4]");

@@ -500,6 +500,14 @@ __device__ __forceinline__ float half_at(const uint8_t* tile_layer, int row, int
 }
 
 template <int kFmt>
+__device__ __forceinline__ float half_bits_to_float(uint16_t bits) {
+  if (kFmt == 1) return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits));
+  return __half2float(*reinterpret_cast<const __half*>(&bits));
+}
+
+// thread j owns feature column j: dwd[j] += sum_r dd[r] * feat[r][j]; dW2[c][j] += sum_r ds[r][c] * hid[r][j].
+// Loads of 8 rows are issued before their FMAs so that 16 requests per thread are in flight.
+template <int kFmt>
 __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
   __shared__ float s_dd[kTileM];
   __shared__ float s_ds[kTileM][4];
@@ -508,6 +516,8 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int blocks_per_tile = A.stash_blocks_per_tile();
   const int j = threadIdx.x;  // feature column
+  const size_t col_off = (size_t)(j >> 6) * kBlkBytes + ((j & 7) << 1);
+  const uint32_t unit = (j >> 3) & 7;
   float acc_wd = 0.f, acc_w2[4] = {0.f, 0.f, 0.f, 0.f}, acc_bd = 0.f, acc_b2 = 0.f;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     __syncthreads();
@@ -526,13 +536,26 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
     }
     __syncthreads();
     const uint8_t* tile = p.stash + (size_t)t * blocks_per_tile * kBlkBytes;
-    const uint8_t* feat = tile + (size_t)A.stash_block_of_layer(n - 1) * kBlkBytes;  // last trunk output
-    const uint8_t* hid = tile + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;   // colour hidden
-    for (int r = 0; r < kTileM; ++r) {
-      acc_wd = fmaf(s_dd[r], half_at<kFmt>(feat, r, j), acc_wd);
-      if (j < kDirPad) {
-        const float h = half_at<kFmt>(hid, r, j);
-        for (int c = 0; c < C; ++c) acc_w2[c] = fmaf(s_ds[r][c], h, acc_w2[c]);
+    const uint8_t* feat = tile + (size_t)A.stash_block_of_layer(n - 1) * kBlkBytes + col_off;  // last trunk output
+    const uint8_t* hid = tile + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes + col_off;   // colour hidden
+    const bool do_hid = j < kDirPad;
+#pragma unroll 1
+    for (int r0 = 0; r0 < kTileM; r0 += 8) {
+      uint16_t f[8], h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        const size_t off = (size_t)r * 128 + ((unit ^ (uint32_t)(r & 7)) << 4);
+        f[i] = __ldg(reinterpret_cast<const uint16_t*>(feat + off));
+        h[i] = do_hid ? __ldg(reinterpret_cast<const uint16_t*>(hid + off)) : (uint16_t)0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        acc_wd = fmaf(s_dd[r], half_bits_to_float<kFmt>(f[i]), acc_wd);
+        const float hv = half_bits_to_float<kFmt>(h[i]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc_w2[c] = fmaf(s_ds[r][c], hv, acc_w2[c]);
       }
     }
     if (j == 0)
@@ -548,7 +571,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
 }
 
 // per-ray direction part of the colour hidden layer: dW_c[:, H + k] += sum_rays (sum_samples dY[ray, s, :]) emb27[ray][k]
-// one warp per ray; lane owns 4 of the 128 hidden columns
+// one warp per ray; lane owns 4 of the 128 hidden columns (one 8-byte load per sample)
 template <int kFmt>
 __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
   __shared__ float s_acc[kDirPad * 28];  // [j][k], 27 direction-embedding channels (+pad)
@@ -560,28 +583,47 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
   for (int i = threadIdx.x; i < kDirPad * 28; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const size_t layer_off = (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
+  const int c0 = lane * 4;  // columns c0..c0+3 live in one 16-byte unit
+  const size_t col_off = (size_t)(c0 >> 6) * kBlkBytes + ((c0 & 7) << 1);
+  const uint32_t unit = (c0 >> 3) & 7;
   for (int64_t ray = (int64_t)blockIdx.x * nw + wib; ray < p.R; ray += (int64_t)gridDim.x * nw) {
     float gsum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < p.P; ++s) {
-      const int64_t gidx = ray * p.P + s;
-      const int64_t t = gidx / kTileM;
-      const int r = (int)(gidx % kTileM);
-      const uint8_t* tile = p.gstash + (size_t)t * blocks_per_tile * kBlkBytes + layer_off;
+#pragma unroll 1
+    for (int s0 = 0; s0 < p.P; s0 += 8) {
+      uint2 v[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) gsum[i] += half_at<kFmt>(tile, r, lane * 4 + i);
+      for (int i = 0; i < 8; ++i) {
+        const int64_t gidx = ray * p.P + min(s0 + i, p.P - 1);
+        const int64_t t = gidx / kTileM;
+        const uint32_t r = (uint32_t)(gidx % kTileM);
+        v[i] = __ldg(reinterpret_cast<const uint2*>(p.gstash + (size_t)t * blocks_per_tile * kBlkBytes + layer_off + col_off +
+                                                    (size_t)r * 128 + ((unit ^ (r & 7)) << 4)));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (s0 + i < p.P) {
+          const float2 a = Half2Pack<kFmt>::unpack(v[i].x), b = Half2Pack<kFmt>::unpack(v[i].y);
+          gsum[0] += a.x; gsum[1] += a.y; gsum[2] += b.x; gsum[3] += b.y;
+        }
+      }
     }
     // direction embedding of this ray (same arithmetic as dirbias_kernel)
     const float dx = p.directions[ray * 3], dy = p.directions[ray * 3 + 1], dz = p.directions[ray * 3 + 2];
     const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
     const float d[3] = {dx / nrm, dy / nrm, dz / nrm};
     const int nf = A.n_freq_dir;
-    for (int k = 0; k < ed; ++k) {
-      float e;
-      if (k < 3 * nf) e = sinf(d[k / nf] * exp2f((float)(k % nf)));
-      else if (k < 6 * nf) e = cosf(d[(k - 3 * nf) / nf] * exp2f((float)((k - 3 * nf) % nf)));
-      else e = d[k - 6 * nf];
+    // lane k (< 27) evaluates embedding channel k once; every lane then reads all of them by shuffle
+    float e_mine = 0.f;
+    if (lane < ed) {
+      const int k = lane;
+      if (k < 3 * nf) e_mine = sinf(d[k / nf] * exp2f((float)(k % nf)));
+      else if (k < 6 * nf) e_mine = cosf(d[(k - 3 * nf) / nf] * exp2f((float)((k - 3 * nf) % nf)));
+      else e_mine = d[k - 6 * nf];
+    }
+    for (int k = 0; k < ed && k < 32; ++k) {
+      const float e = __shfl_sync(0xffffffffu, e_mine, k);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[(lane * 4 + i) * 28 + k], gsum[i] * e);
+      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[(c0 + i) * 28 + k], gsum[i] * e);
     }
   }
   __syncthreads();
@@ -610,9 +652,9 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
     cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
     dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
     wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
-    heads<<<(int)(n_tiles < 2 * sms ? n_tiles : 2 * sms), 256, 0, stream>>>(p);
+    heads<<<(int)(n_tiles < 4 * sms ? n_tiles : 4 * sms), 256, 0, stream>>>(p);
     const int64_t ray_blocks = (p.R + 7) / 8;
-    dir<<<(int)(ray_blocks < sms ? ray_blocks : sms), 256, 0, stream>>>(p);
+    dir<<<(int)(ray_blocks < 2 * sms ? ray_blocks : 2 * sms), 256, 0, stream>>>(p);
   };
   if (A.fmt == 1)
     run(mlp_bwd_dgrad_kernel<1>, mlp_bwd_wgrad_kernel<1>, mlp_bwd_heads_kernel<1>, mlp_bwd_dir_kernel<1>);
