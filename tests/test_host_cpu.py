@@ -1,0 +1,190 @@
+"""CPU tests of the host side: the C ABI loads and exports every declared symbol (no compute calls), argument
+validation and error mapping, config / registry (the plugin boundary), the chunkify contract, losses."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(REPO, "tests", "configs")
+
+
+# --------------------------------------------------------------------------- C ABI
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "yanerf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(yn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from yanerf import _native as N
+
+    lib = N.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/yanerf_b200.h but not exported"
+    assert sorted(N.SYMBOLS) == declared, "ctypes prototypes out of sync with the header"
+    assert lib.yn_version() == 1
+
+
+def test_size_queries_and_validation_without_gpu():
+    from yanerf import _native as N
+
+    lib = N.lib()
+    lego = N.MlpArch(8, 1 << 5, 10, 4, 256, 128, 3, N.FMT_FP16)
+    assert lib.yn_mlp_param_count(ctypes.byref(lego)) == 595844
+    n_stages_fwd = 2 + 4 * 10 + 10 + 2 * 10 + 10 + 4  # incl. one 4 KB bias block per half of hidden-only layers
+    assert lib.yn_mlp_wpack_bytes(ctypes.byref(lego)) >= n_stages_fwd * 16384
+    assert lib.yn_mlp_aux_floats(ctypes.byref(lego)) == 9 * 256 + 256 + 4 + 512 + 4
+    assert lib.yn_mlp_stash_bytes(ctypes.byref(lego), 1000) == 8 * (1 + 36 + 2) * 16384
+    bad = N.MlpArch(8, 1 << 5, 12, 4, 256, 128, 3, N.FMT_FP16)  # 75-channel embedding
+    assert lib.yn_mlp_param_count(ctypes.byref(bad)) == -1
+    assert b"embedding" in lib.yn_last_error_string()
+    rc = lib.yn_mlp_fwd(ctypes.byref(bad), *([None] * 9), 1, 1, None)
+    assert rc == -2
+    with pytest.raises(NotImplementedError):
+        N.check(rc)
+    cfg = N.MarchCfg()
+    cfg.bg_channels = 2
+    rc = lib.yn_composite_fwd(ctypes.byref(cfg), *([None] * 10), 4, 8, 3, None)
+    assert rc == -1 and b"Wrong number of background color channels" in lib.yn_last_error_string()
+    with pytest.raises(ValueError):
+        N.check(rc)
+    assert lib.yn_sample_pdf_merge(None, None, None, 0, None, None, None, 4, 2, 8, 1, None) == -1  # P < 3
+    assert lib.yn_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -1  # step < 1
+
+
+def test_ops_refuse_cpu_tensors():
+    from yanerf import ops
+
+    cfg = ops.march_cfg(1e10, 0.0, 0.0, False, False, (0.0,))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.composite(torch.zeros(2, 4), torch.zeros(2, 4, 3), torch.zeros(2, 4), torch.ones(2, 3), cfg)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.sample_pdf_merge(torch.zeros(2, 8), torch.ones(2, 8), 4, None)
+
+
+# --------------------------------------------------------------------------- config / registry
+def test_config_inheritance_templates_and_overrides():
+    from yanerf.utils.config import Config, DictAction
+
+    cfg = Config.fromfile(os.path.join(CFG, "child.yml"))
+    assert cfg.seed == 7 and cfg.pipeline.type == "NeRFPipeline"
+    assert cfg.pipeline.chunk_size_grid == 1024 and cfg.pipeline.num_passes == 2
+    assert cfg.pipeline.renderer.density_noise_std_train == 0.2 and cfg.pipeline.renderer.n_pts_per_ray_fine_training == 8
+    assert cfg.here == CFG
+    cfg.merge_from_dict({"pipeline.renderer.bg_color": [1.0], "lists.1.a": 5, "new.key": "x"})
+    assert cfg.pipeline.renderer.bg_color == [1.0] and cfg.lists[1].a == 5 and cfg.new.key == "x"
+    assert "NeRFPipeline" in cfg.pretty_text
+    py = Config.fromfile(os.path.join(CFG, "py_cfg.py"))
+    assert py.pipeline.num_passes == 3 and py.pipeline.renderer.type == "MultipassEmissionAbsorpsionRenderer"
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg_options", nargs="+", action=DictAction)
+    ns = ap.parse_args(["--cfg_options", "a.b=1", "c=[1,2.5,x]", "d=(1,2)", "e=true", "f=None"])
+    assert ns.cfg_options == {"a.b": 1, "c": [1, 2.5, "x"], "d": (1, 2), "e": True, "f": None}
+    with pytest.raises(FileNotFoundError):
+        Config.fromfile(os.path.join(CFG, "missing.yml"))
+
+
+def test_registry_contract():
+    from yanerf.utils.registry import Registry
+
+    reg = Registry("things")
+
+    @reg.register_module()
+    class Thing:
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+
+    t = reg.build(dict(type="Thing", x=1))
+    assert (t.x, t.y) == (1, 2)
+    with pytest.raises(KeyError, match="Nope is not in the things registry"):
+        reg.build(dict(type="Nope"))
+    with pytest.raises(TypeError, match="Thing: "):
+        reg.build(dict(type="Thing", z=3))
+    with pytest.raises(KeyError):
+        reg.register_module()(Thing)
+    reg.register_module(force=True)(Thing)
+    from yanerf.pipelines import PIPELINES
+    from yanerf.pipelines.feature_extractors import FEATURE_EXTRACTORS
+    from yanerf.pipelines.models import MODELS
+    from yanerf.pipelines.ray_samplers import RAY_SAMPLERS
+    from yanerf.pipelines.renderers import RENDERERS
+
+    assert "NeRFPipeline" in PIPELINES and "RaySampler" in RAY_SAMPLERS and "IdentityMapper" in FEATURE_EXTRACTORS
+    assert "NeRFMLP" in MODELS and "ZeroOutputer" in MODELS and "MultipassEmissionAbsorpsionRenderer" in RENDERERS
+
+
+def test_pipeline_builds_with_reference_state_dict_layout():
+    from yanerf.testing import build_pipeline
+
+    pipe = build_pipeline(800, 800, 4096, 128, 0.2, 131072)
+    sd = pipe.state_dict()
+    assert len(sd) == 48 and sum(v.numel() for v in sd.values()) == 1191688
+    assert sd["implicit_functions.0._fn.xyz_encoder.mlp.5.0.weight"].shape == (256, 319)
+    assert sd["implicit_functions.1._fn.color_layer.0.weight"].shape == (128, 283)
+    assert sd["implicit_functions.1._fn.density_layer.bias"].abs().sum() == 0
+    assert "bg_color" not in sd  # non-persistent buffers
+
+
+# --------------------------------------------------------------------------- chunkify contract
+def test_chunk_plan_and_generator_round_trip():
+    from yanerf.pipelines.nerf_pipeline import _chunk_generator, _tensor_collator, cat_dataclass, chunk_plan
+    from yanerf.pipelines.renderers.utils import RendererOutput
+
+    assert chunk_plan(640000, 64, 131072) == (313, 2045)  # lego 800x800
+    assert chunk_plan(190512, 64, 131072) == (94, 2027)   # fern 378x504
+    B, H, W, P = 2, 5, 7, 4
+    o, d = torch.rand(B, H, W, 3), torch.rand(B, H, W, 3)
+    z, xy, bg = torch.rand(B, H, W, P), torch.rand(B, H, W, 2), torch.rand(B, H, W, 3)
+    chunks = list(_chunk_generator(3 * P, o, d, z, xy, bg, flag=True))
+    assert len(chunks) == 12 and all(kw == {"flag": True} for _, kw in chunks)
+    assert chunks[0][0][0].shape == (B, 3, 1, 3) and chunks[-1][0][2].shape == (B, 2, 1, P)
+    outs = [RendererOutput(features=a[0] * 2, depths=a[2][..., :1], alpha_masks=a[2][..., 1:2],
+                           aux={"weights": a[2]}, prev_stage=RendererOutput(a[1], a[2][..., :1], a[2][..., :1]))
+            for a, _ in chunks]
+    merged = cat_dataclass(outs, lambda pieces: _tensor_collator(pieces, z.shape[:-1]))
+    assert torch.equal(merged.features, o * 2) and torch.equal(merged.aux["weights"], z)
+    assert torch.equal(merged.prev_stage.features, d) and merged.normals is None
+    assert dataclasses.is_dataclass(merged.prev_stage)
+
+
+# --------------------------------------------------------------------------- losses / pixel gather
+def test_sample_grid_scatter_and_metrics():
+    from yanerf.pipelines.ray_samplers.utils import get_xy_grid
+    from yanerf.pipelines.utils import ViewMetrics, huber, sample_grid, scatter_rays_to_image
+
+    B, H, W = 2, 6, 10
+    img = torch.rand(B, H, W, 3)
+    grid = get_xy_grid(H, W)[None].expand(B, -1, -1, -1)
+    assert grid[0, 2, 3].tolist() == [3.0, 2.0]
+    assert torch.equal(sample_grid(img, grid), img)
+    mask = torch.rand(H, W) > 0.5
+    xy = grid[:, mask][:, :, None]  # [B, n, 1, 2]
+    assert torch.equal(sample_grid(img, xy)[:, :, 0], img[:, mask])
+    canvas = scatter_rays_to_image(sample_grid(img, xy), xy, H, W)
+    assert torch.equal(canvas[:, mask], img[:, mask]) and canvas[:, ~mask].abs().sum() == 0
+    with pytest.raises(AssertionError):
+        sample_grid(img, grid + 100.0)
+    m = ViewMetrics()(image_sampling_grid=grid, images=img, images_pred=img * 0.5)
+    assert set(m) == {"loss_rgb_huber", "loss_rgb_mse"} and m["loss_rgb_mse"].shape == (B,)
+    torch.testing.assert_close(m["loss_rgb_mse"], ((img * 0.5) ** 2).reshape(B, -1).mean(-1))
+    torch.testing.assert_close(huber(torch.tensor([0.0])), torch.tensor([(1.0001 ** 0.5 - 1) * 0.03]))
+    assert ViewMetrics()(image_sampling_grid=grid, images=None, images_pred=img) == {}
+
+
+def test_lr_schedule_and_stats():
+    from yanerf.runners.apis import create_stats
+    from yanerf.runners.engine import exponential_lr
+
+    assert exponential_lr(0, 5e-4, 5e-5, 200000) == 5e-4
+    assert abs(exponential_lr(200000, 5e-4, 5e-5, 200000) - 5e-5) < 1e-12
+    assert abs(exponential_lr(500, 5e-4, 5e-5, 200000, warmup_iters=1000, warmup_lr=1e-5) - (1e-5 + 4.9e-4 * 0.5)) < 1e-12
+    st = create_stats({"loss_rgb_mse": torch.tensor([0.01, 0.01]), "objective": torch.tensor([0.5]), "rendered_images": torch.zeros(1)})
+    assert abs(st["loss_rgb_psnr"] - 20.0) < 1e-4 and st["objective"] == 0.5 and "rendered_images" not in st

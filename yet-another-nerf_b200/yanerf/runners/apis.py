@@ -1,0 +1,74 @@
+"""Thin re-host of the reference's runner loop (`yanerf/runners/apis.py:30-236`, `runners/utils.py:257-283`) on
+top of `FusedTrainer`: same call structure (`inference` -> `model(**data, evaluation_mode=...)`), same stats
+(`create_stats`: mean of every loss_/objective key, PSNR from every "mse" key), same eval sharding (one image per
+rank, all-gather of the `(B,)` losses, truncation to the dataset length).  Data loading, PNG dumps, hooks and
+checkpoint rotation stay with the caller (`scripts/run.py`), as in the reference."""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from yanerf.pipelines.utils import EvaluationMode
+
+from .engine import FusedTrainer, exponential_lr
+
+
+def inference(model: torch.nn.Module, data: Dict[str, Any], evaluation_mode: EvaluationMode, compute_metrics: bool = True):
+    return model(**data, evaluation_mode=evaluation_mode)
+
+
+def create_stats(preds: Dict[str, Any]) -> Dict[str, float]:
+    stats = {}
+    for k, v in preds.items():
+        if torch.is_tensor(v) and (k.startswith("loss_") or k.startswith("objective")):
+            stats[k] = float(v.detach().float().mean())
+    for k in [k for k in stats if "mse" in k]:
+        stats[k.replace("mse", "psnr")] = -10.0 * math.log10(max(stats[k], 1e-12))
+    return stats
+
+
+@torch.no_grad()
+def concat_all_gather(t: torch.Tensor) -> torch.Tensor:
+    """all_gather along dim 0 (identity without an initialised process group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts, dim=0)
+
+
+def train_one_epoch(trainer: FusedTrainer, batches: Iterable[Dict[str, Any]], config: Dict[str, Any], epoch: int = 0,
+                    iters_per_epoch: Optional[int] = None) -> Dict[str, float]:
+    """One pass over `batches` (dicts of device tensors keyed like the dataset NamedTuples)."""
+    world = trainer.world
+    lr, min_lr = config.get("lr", 5e-4) * world, config.get("min_lr", 5e-5) * world  # scripts/run.py:152-156
+    num_iters = config.get("num_iters", 200000)
+    it = epoch * (iters_per_epoch or 0)
+    trainer.pipeline.train()
+    preds: Dict[str, Any] = {}
+    for data in batches:
+        step_lr = exponential_lr(it, lr, min_lr, num_iters, config.get("warmup_steps", 0), config.get("warmup_lr", 0.0))
+        preds = trainer.train_step(data, lr=step_lr)
+        it += 1
+    return create_stats(preds)
+
+
+@torch.no_grad()
+def eval_one_epoch(model: torch.nn.Module, batches: Iterable[Dict[str, Any]], dataset_len: Optional[int] = None) -> Dict[str, float]:
+    model.eval()
+    gathered: Dict[str, list] = {}
+    for data in batches:
+        preds = inference(model, data, EvaluationMode.EVALUATION)
+        for k, v in preds.items():
+            if torch.is_tensor(v) and (k.startswith("loss_") or k.startswith("objective")):
+                gathered.setdefault(k, []).append(concat_all_gather(v))
+    out = {}
+    for k, vs in gathered.items():
+        allv = torch.cat(vs, dim=0)
+        if dataset_len is not None:
+            allv = allv[:dataset_len]
+        out[k] = allv
+    return create_stats(out)
