@@ -155,11 +155,41 @@ def run_reference_arm(args):
                         "note": "reference algorithm on host cores (oracle port), bounded ray sample per step"},
                 cpu_baseline=base,
                 e2e={"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+class StdoutToStderr:
+    """Everything written to fd 1 while the bench runs (NCCL banners, library chatter) goes to stderr, so that
+    stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def emit(line) -> None:
+    EMIT.append(json.dumps(line))
+
+
+EMIT = []
 
 
 # --------------------------------------------------------------------------- GPU arm
 def main():
+    with StdoutToStderr():
+        _main()
+    for text in EMIT:
+        print(text, flush=True)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -293,7 +323,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 if __name__ == "__main__":

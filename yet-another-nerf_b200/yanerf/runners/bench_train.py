@@ -91,7 +91,7 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
                       "frac": round(achieved / peaks["tensor"], 4), "traffic": None,
                       "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in prof.items()}},
         )
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
