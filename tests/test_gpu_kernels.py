@@ -357,3 +357,29 @@ def test_mlp_backward_vs_oracle_autograd(name, R, P, dtype):
             assert rel <= tol and cos >= mincos, f"{k} vs {tag}: rel L2 {rel:.3e}, cos {cos:.6f}, |ref| {float(gr.norm()):.3e}"
     print(f"{name} R={R} P={P} {dtype}: worst rel L2 gradient error {worst['rounded']:.2e} (operand-rounded oracle), "
           f"{worst['fp32']:.2e} (fp32 oracle)")
+
+
+def test_composite_generic_and_blocked_paths_agree():
+    """P in {64,128,192} with 8-byte aligned rows takes the lane-blocked kernels, anything else the chunked ones:
+    feed the same rays through both (the second copy is deliberately misaligned by one float)."""
+    from yanerf import ops
+
+    rs = np.random.RandomState(3)
+    R, P = 300, 128
+    mk = lambda *s: torch.from_numpy(rs.uniform(size=s).astype(np.float32)).to(DEV)
+    sig, rgb, z, d = mk(R, P) * 4 - 1, mk(R, P, 3), torch.sort(2 + 4 * mk(R, P), dim=-1)[0], mk(R, 3) - 0.5
+    cfg = ops.march_cfg(1e10, 1e-6, 0.0, False, False, (0.1, 0.2, 0.3))
+
+    def misaligned(t):
+        buf = torch.empty(t.numel() + 1, device=DEV)
+        buf[1:].copy_(t.reshape(-1))
+        return buf[1:].view(t.shape)
+
+    outs = []
+    for f in (lambda t: t, misaligned):
+        a, b = f(sig).detach().requires_grad_(True), f(rgb).detach().requires_grad_(True)
+        feats, dep, op, w = ops.composite(a, b, f(z), d, cfg)
+        (feats.sum() + 0.3 * dep.sum() + (w * w).sum()).backward()
+        outs.append((feats, dep, op, w, a.grad, b.grad))
+    for x, y, name in zip(outs[0], outs[1], ("features", "depths", "opacities", "weights", "d_sigma", "d_rgb")):
+        close(x, y.detach().cpu(), 2e-5, 2e-6, name)

@@ -235,6 +235,20 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const MarchParams p)
   }
 }
 
+}  // namespace ynb
+#include "composite_blocked.cuh"
+namespace ynb {
+
+static bool aligned8(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; }
+// lane-blocked fast path: lego / fern shapes, 3 channels, 8-byte aligned rows
+static int blocked_S(const MarchParams& p) {
+  if (p.C != 3 || (p.P != 64 && p.P != 128 && p.P != 192)) return 0;
+  const void* ptrs[] = {p.sigma, p.rgb, p.z, p.noise, p.weights, p.d_weights, p.d_sigma, p.d_rgb};
+  for (const void* q : ptrs)
+    if (!aligned8(q)) return 0;
+  return p.P / 32;
+}
+
 static int validate(const char* name, const yn_march_cfg* cfg, int64_t R, int P, int C) {
   if (!cfg) return fail(YN_ERR_INVALID_ARGUMENT, "%s: null config", name);
   if (R < 0 || P < 1 || C < 1 || C > 4) return fail(YN_ERR_INVALID_ARGUMENT, "%s: bad sizes R=%lld P=%d C=%d", name, (long long)R, P, C);
@@ -261,10 +275,12 @@ extern "C" int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_densit
   const int wpb = 8;
   const unsigned grid = (unsigned)((R + wpb - 1) / wpb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (P == 64) ynb::composite_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(p);
-  else if (P == 128) ynb::composite_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(p);
-  else if (P == 192) ynb::composite_fwd_kernel<6><<<grid, wpb * 32, 0, st>>>(p);
-  else ynb::composite_fwd_kernel<0><<<grid, wpb * 32, 0, st>>>(p);
+  switch (ynb::blocked_S(p)) {
+    case 2: ynb::composite_fwd_blocked_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 4: ynb::composite_fwd_blocked_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 6: ynb::composite_fwd_blocked_kernel<6><<<grid, wpb * 32, 0, st>>>(p); break;
+    default: ynb::composite_fwd_kernel<0><<<grid, wpb * 32, 0, st>>>(p);
+  }
   return ynb::check_launch("yn_composite_fwd");
 }
 
@@ -284,6 +300,13 @@ extern "C" int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_densit
   p.d_sigma = d_raw_density; p.d_rgb = d_rgb;
   p.R = R; p.P = P; p.C = C;
   const int wpb = 8;
-  ynb::composite_bwd_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const unsigned grid = (unsigned)((R + wpb - 1) / wpb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (ynb::blocked_S(p)) {
+    case 2: ynb::composite_bwd_blocked_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 4: ynb::composite_bwd_blocked_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 6: ynb::composite_bwd_blocked_kernel<6><<<grid, wpb * 32, 0, st>>>(p); break;
+    default: ynb::composite_bwd_kernel<<<grid, wpb * 32, 0, st>>>(p);
+  }
   return ynb::check_launch("yn_composite_bwd");
 }

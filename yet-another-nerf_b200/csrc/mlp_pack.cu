@@ -114,51 +114,51 @@ __global__ void pack_aux_kernel(const Arch A, const float* __restrict__ params, 
   aux[i] = v;
 }
 
-// one block = 8 rays x 128 outputs
+// one block = 32 rays x 128 outputs: the 27-channel embeddings of the 32 rays are built cooperatively in shared
+// memory, then thread j keeps its weight row in registers and walks the rays (coalesced 512-byte stores)
 __global__ void __launch_bounds__(128) dirbias_kernel(const Arch A, const float* __restrict__ params,
                                                      const float* __restrict__ directions,
                                                      float* __restrict__ dirbias, int64_t R) {
-  __shared__ float s_emb[8][64];
-  __shared__ float s_w[kDirPad * 64];
-  const int ed = A.embed_dir();
+  constexpr int kRays = 32;
+  __shared__ float s_emb[kRays][33];
+  __shared__ float s_dir[kRays][3];
+  const int ed = A.embed_dir();  // <= 32 (check_arch)
+  const int nf = A.n_freq_dir;
   const int din = A.din(A.n_layers + 1);
   const float* W = params + A.w_offset(A.n_layers + 1);
-  const float* bc = params + A.b_offset(A.n_layers + 1);
-  for (int i = threadIdx.x; i < A.hidden_dir * ed; i += blockDim.x) {
-    const int j = i / ed, k = i % ed;
-    s_w[j * 64 + k] = W[(int64_t)j * din + A.hidden_last + k];
-  }
-  const int64_t ray0 = (int64_t)blockIdx.x * 8;
-  if (threadIdx.x < 8) {
-    const int64_t ray = ray0 + threadIdx.x;
+  const int j = threadIdx.x;
+  float w[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) w[k] = (j < A.hidden_dir && k < ed) ? __ldg(W + (int64_t)j * din + A.hidden_last + k) : 0.f;
+  const float bj = j < A.hidden_dir ? __ldg(params + A.b_offset(A.n_layers + 1) + j) : 0.f;
+  const int64_t ray0 = (int64_t)blockIdx.x * kRays;
+  if (j < kRays) {
+    const int64_t ray = ray0 + j;
+    float d[3] = {0.f, 0.f, 0.f};
     if (ray < R) {
       // F.normalize(d, dim=-1) = d / max(|d|, 1e-12)  (nerf_mlp.py:105)
       const float dx = directions[ray * 3], dy = directions[ray * 3 + 1], dz = directions[ray * 3 + 2];
       const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
-      const float d[3] = {dx / nrm, dy / nrm, dz / nrm};
-      const int nf = A.n_freq_dir;
-      for (int a = 0; a < 3; ++a) {
-        float f = 1.f;
-        for (int k = 0; k < nf; ++k, f *= 2.f) {
-          float s, c;
-          sincosf(d[a] * f, &s, &c);
-          s_emb[threadIdx.x][a * nf + k] = s;
-          s_emb[threadIdx.x][3 * nf + a * nf + k] = c;
-        }
-        s_emb[threadIdx.x][6 * nf + a] = d[a];
-      }
+      d[0] = dx / nrm; d[1] = dy / nrm; d[2] = dz / nrm;
     }
+    s_dir[j][0] = d[0]; s_dir[j][1] = d[1]; s_dir[j][2] = d[2];
   }
   __syncthreads();
-  const int j = threadIdx.x;
-  for (int i = 0; i < 8; ++i) {
-    const int64_t ray = ray0 + i;
+  for (int i = threadIdx.x; i < kRays * ed; i += blockDim.x) {
+    const int r = i / ed, k = i % ed;
+    float e;
+    if (k < 3 * nf) e = sinf(s_dir[r][k / nf] * exp2f((float)(k % nf)));
+    else if (k < 6 * nf) e = cosf(s_dir[r][(k - 3 * nf) / nf] * exp2f((float)((k - 3 * nf) % nf)));
+    else e = s_dir[r][k - 6 * nf];
+    s_emb[r][k] = e;
+  }
+  __syncthreads();
+  for (int r = 0; r < kRays; ++r) {
+    const int64_t ray = ray0 + r;
     if (ray >= R) break;
-    float acc = 0.f;
-    if (j < A.hidden_dir) {
-      acc = bc[j];
-      for (int k = 0; k < ed; ++k) acc = fmaf(s_w[j * 64 + k], s_emb[i][k], acc);
-    }
+    float acc = bj;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(w[k], k < ed ? s_emb[r][k] : 0.f, acc);
     dirbias[ray * kDirPad + j] = acc;
   }
 }
@@ -188,7 +188,7 @@ extern "C" int yn_mlp_dirbias(const yn_mlp_arch* arch, const float* params, cons
   if (R == 0) return YN_OK;
   if (!params || !directions || !dirbias) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_dirbias: null pointer");
   const ynb::Arch A = ynb::arch_from_c(arch);
-  ynb::dirbias_kernel<<<(unsigned)((R + 7) / 8), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, params, directions,
+  ynb::dirbias_kernel<<<(unsigned)((R + 31) / 32), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, params, directions,
                                                                                          dirbias, R);
   return ynb::check_launch("yn_mlp_dirbias");
 }
