@@ -383,3 +383,40 @@ def test_composite_generic_and_blocked_paths_agree():
         outs.append((feats, dep, op, w, a.grad, b.grad))
     for x, y, name in zip(outs[0], outs[1], ("features", "depths", "opacities", "weights", "d_sigma", "d_rgb")):
         close(x, y.detach().cpu(), 2e-5, 2e-6, name)
+
+
+@pytest.mark.parametrize("P,n", [(64, 128), (64, 64), (128, 128), (128, 64), (192, 128), (192, 64)])
+def test_refiner_fast_and_generic_kernels_agree_bitwise(P, n):
+    """The lane-blocked fast path (aligned rows, lego / fern shapes) and the generic kernel (forced here by a
+    one-float misalignment of the output) must produce identical bits, random and deterministic draws, sorted and
+    unsorted input depths."""
+    from yanerf import ops
+
+    rs = np.random.RandomState(P + n)
+    R = 3000
+    z = np.sort(2 + 4 * rs.uniform(size=(R, P)).astype(np.float32), axis=-1)
+    z[5] = z[5, ::-1].copy()  # one descending row: exercises the unsorted-input fallback
+    w = rs.uniform(size=(R, P)).astype(np.float32) ** 8
+    w[rs.uniform(size=w.shape) < 0.5] = 0.0
+    u = np.minimum(rs.uniform(size=(R, n)).astype(np.float32), np.float32(1 - 2 ** -24))
+    zt, wt, ut = T(z).to(DEV), T(w).to(DEV), T(u).to(DEV)
+    for uu in (None, ut):
+        fast, inds_f, _ = ops.sample_pdf_merge(zt, wt, n, uu, want_inds=True)
+        buf = torch.empty(R * (P + n) + 1, device=DEV)
+        out = buf[1:].view(R, P + n)
+        inds_g = torch.empty(R, n, dtype=torch.int64, device=DEV)
+        flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+        uarg, stride = (ops.det_draws(n, zt.device), 0) if uu is None else (uu, n)
+        ops._call("yn_sample_pdf_merge", ops.N.ptr(zt), ops.N.ptr(wt), ops.N.ptr(uarg), stride,
+                  ctypes_ptr(out), ops.N.ptr(inds_g, torch.int64), ops.N.ptr(flag, torch.int32), R, P, n, 1, ops.N.stream_ptr())
+        same(inds_f, inds_g.cpu(), "inds")
+        same(fast, out.cpu(), "lengths")
+        ref, ref_inds = O.refine_lengths(T(z), T(w), n, None if uu is None else T(u))
+        same(inds_f, ref_inds, "inds vs oracle")
+        same(fast, ref, "lengths vs oracle")
+
+
+def ctypes_ptr(t):
+    import ctypes
+
+    return ctypes.c_void_p(t.data_ptr())

@@ -12,8 +12,9 @@
 //     accumulators 1..3 folded into 0, then the scalar tail summed from zero, then the 8 lanes in order;
 //   * cumsum = fp64 running sum, each prefix rounded to fp32;
 //   * every other op is a single correctly rounded fp32 operation (no FMA contraction).
-// The fp64 prefix is computed with a parallel scan; whenever a prefix lands within 1e-12 of an fp32 rounding
-// boundary (where the association order could matter) the warp redoes that ray sequentially.
+// The fp64 prefix is computed with a parallel scan whose result can differ from the sequential fp64 sum by at most
+// (K-1) 2^-53 relative (< 1e-14 for K < 100); whenever a prefix lands within 4e-14 relative of an fp32 rounding
+// boundary (where that difference could change the rounded value) the warp redoes that ray sequentially.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -114,6 +115,59 @@ __device__ void warp_bitonic_sort(float* a, int n, int lane) {
   }
 }
 
+// bitonic sort of 32*NPL floats held in registers, element e = lane*NPL + r; partners inside a lane are
+// compare-swapped in registers, partners in other lanes through one shuffle per element
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_sort_regs(float (&v)[NPL], int lane) {
+  constexpr int N = 32 * NPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j < NPL) {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const int pr = r ^ j;
+          if (pr > r) {
+            const bool up = ((lane * NPL + r) & k) == 0;
+            const float a = v[r], b = v[pr];
+            const bool sw = (a > b) == up;
+            v[r] = sw ? b : a;
+            v[pr] = sw ? a : b;
+          }
+        }
+      } else {
+        const int lj = j / NPL;
+        const bool lower = (lane & lj) == 0;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          const bool up = ((lane * NPL + r) & k) == 0;
+          v[r] = (lower == up) ? fminf(v[r], other) : fmaxf(v[r], other);
+        }
+      }
+    }
+  }
+}
+
+// sorts s_new[0 .. 32*NPL) ascending (skipped when already sorted, the usual case for deterministic draws)
+template <int NPL>
+__device__ __forceinline__ void sort_new_samples(float* s_new, int lane) {
+  float v[NPL];
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) v[r] = s_new[lane * NPL + r];
+  bool ok = true;
+#pragma unroll
+  for (int r = 0; r + 1 < NPL; ++r) ok &= v[r] <= v[r + 1];
+  const float nxt = __shfl_down_sync(0xffffffffu, v[0], 1);
+  ok &= (lane == 31) || (v[NPL - 1] <= nxt);
+  if (__all_sync(0xffffffffu, ok)) return;
+  warp_bitonic_sort_regs<NPL>(v, lane);
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) s_new[lane * NPL + r] = v[r];
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
@@ -183,7 +237,7 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p
       const double fu = static_cast<double>(nextafterf(f, CUDART_INF_F));
       const double fd = static_cast<double>(nextafterf(f, -CUDART_INF_F));
       const double mid_up = 0.5 * (static_cast<double>(f) + fu), mid_dn = 0.5 * (static_cast<double>(f) + fd);
-      ambiguous |= (mid_up - incl < 1e-12) || (incl - mid_dn < 1e-12);
+      ambiguous |= (mid_up - incl < 4e-14 * incl) || (incl - mid_dn < 4e-14 * incl);
     }
     __syncwarp();
     if (k < K) s_cdf[k + 1] = f;  // overwrites wp[k], already consumed by every lane of this chunk
@@ -246,11 +300,17 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p
     for (int i = lane; i < total_n; i += 32) outr[i] = s_new[i];
     return;
   }
-  int n2 = 1;
-  while (n2 < N) n2 <<= 1;
-  for (int i = N + lane; i < n2; i += 32) s_new[i] = CUDART_INF_F;
-  __syncwarp();
-  warp_bitonic_sort(s_new, n2, lane);
+  if (N == 128) {
+    sort_new_samples<4>(s_new, lane);
+  } else if (N == 64) {
+    sort_new_samples<2>(s_new, lane);
+  } else {
+    int n2 = 1;
+    while (n2 < N) n2 <<= 1;
+    for (int i = N + lane; i < n2; i += 32) s_new[i] = CUDART_INF_F;
+    __syncwarp();
+    warp_bitonic_sort(s_new, n2, lane);
+  }
   // merge path: rank of every element in the union (coarse first on ties)
   for (int i = lane; i < P; i += 32) {
     const float v = s_z[i];
@@ -274,6 +334,19 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p
 
 }  // namespace ynb
 
+#include "sample_pdf_fast.cuh"
+
+template <int PS, int NPL>
+static void launch_fast(const ynb::PdfParams& p, cudaStream_t st) {
+  constexpr int P = 32 * PS;
+  constexpr int CDFN = P <= 64 ? 64 : (P <= 128 ? 128 : 256);
+  const int wpb = 8;
+  const size_t smem = (size_t)wpb * (CDFN + 2 * P + p.sort_pow2) * sizeof(float);
+  auto kern = ynb::sample_pdf_merge_fast_kernel<PS, NPL>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(unsigned)((p.R + wpb - 1) / wpb), wpb * 32, smem, st>>>(p);
+}
+
 static int launch_pdf(const float* lengths, const float* weights, const float* u, int64_t u_row_stride,
                       float* new_lengths, int64_t* inds, int32_t* flag, int64_t R, int P, int n_new,
                       int add_input_samples, int bins_mode, int sort_out, void* stream) {
@@ -292,11 +365,28 @@ static int launch_pdf(const float* lengths, const float* weights, const float* u
   p.sort_pow2 = n2;
   p.bins_mode = bins_mode;
   p.sort_out = sort_out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+  if (!bins_mode && add_input_samples && sort_out && al8(lengths) && al8(weights) && al8(u) && al8(new_lengths) &&
+      (u_row_stride % 2 == 0)) {
+    const int key = P * 1000 + n_new;
+    bool done = true;
+    switch (key) {
+      case 64128: launch_fast<2, 4>(p, st); break;
+      case 64064: launch_fast<2, 2>(p, st); break;
+      case 128128: launch_fast<4, 4>(p, st); break;
+      case 128064: launch_fast<4, 2>(p, st); break;
+      case 192128: launch_fast<6, 4>(p, st); break;
+      case 192064: launch_fast<6, 2>(p, st); break;
+      default: done = false;
+    }
+    if (done) return ynb::check_launch("yn_sample_pdf_merge");
+  }
   const int wpb = 8;
   const size_t smem = (size_t)wpb * (3 * P + n2) * sizeof(float);
   if (smem > 200 * 1024) return ynb::fail(YN_ERR_UNSUPPORTED, "yn_sample_pdf_merge: P + n_new too large for shared memory");
   cudaFuncSetAttribute(ynb::sample_pdf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ynb::sample_pdf_merge_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  ynb::sample_pdf_merge_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, smem, st>>>(p);
   return ynb::check_launch("yn_sample_pdf_merge");
 }
 
