@@ -31,6 +31,9 @@ for _p in (REPO, os.path.join(REPO, "yet-another-nerf_b200")):
 
 import torch  # noqa: E402
 
+if __name__ == "__main__":  # `import bench` from helpers must see this module instance (EMIT, peaks, ...)
+    sys.modules.setdefault("bench", sys.modules["__main__"])
+
 H = W = 800
 N_COARSE, N_FINE = 64, 128
 FLOP_PER_POINT_FWD = 2 * 589_952

@@ -86,6 +86,9 @@ class NeRFPipeline(torch.nn.Module):
     # see module docstring
     coalesce_chunks: bool = True
     max_points_per_launch: int = 64 << 20
+    # True = the reference's per-call range assertions on the pixel grid (device->host syncs).  FusedTrainer turns
+    # it off: a grid produced by this pipeline's own ray sampler is checked against the image size on the host.
+    validate_pixel_grid: bool = True
 
     def __init__(
         self,
@@ -163,7 +166,15 @@ class NeRFPipeline(torch.nn.Module):
             image_height=image_height, image_width=image_width, min_depth=min_depth, max_depth=max_depth,
         )
         xys = ray_bundle.xys
-        bg_color = sample_grid(bg_image_rgb, xys) if bg_image_rgb is not None else None
+        validate = self.validate_pixel_grid
+        if not validate:
+            gh = image_height if (image_height is not None and image_width is not None) else self.render_image_height
+            gw = image_width if (image_height is not None and image_width is not None) else self.render_image_width
+            for t in (bg_image_rgb, image_rgb, depth_map):
+                if t is not None:
+                    assert gw <= t.shape[-2], "Invalid ray_sampler.image_width"
+                    assert gh <= t.shape[-3], "Invalid ray_sampler.image_height"
+        bg_color = sample_grid(bg_image_rgb, xys, validate) if bg_image_rgb is not None else None
 
         extracted = collections.defaultdict(list)
         for extractor in self.feature_extractors:
@@ -188,7 +199,8 @@ class NeRFPipeline(torch.nn.Module):
             for fn in self.implicit_functions:
                 fn.unbind_args()
 
-        preds = self._get_view_metrics(raymarched=rendered, xys=xys, image_rgb=image_rgb, depth_map=depth_map)
+        preds = self._get_view_metrics(raymarched=rendered, xys=xys, image_rgb=image_rgb, depth_map=depth_map,
+                                       validate_grid=validate)
         blob = {}
         if masked:
             if self.output_rasterized_mc:
@@ -220,13 +232,14 @@ class NeRFPipeline(torch.nn.Module):
         return self.renderer(origins=origins, directions=directions, lengths=lengths, xys=xys, bg_color=bg_color, **kwargs)
 
     # ------------------------------------------------------------------ losses
-    def _get_view_metrics(self, raymarched: RendererOutput, xys, image_rgb=None, depth_map=None, keys_prefix: str = "loss_"):
+    def _get_view_metrics(self, raymarched: RendererOutput, xys, image_rgb=None, depth_map=None, keys_prefix: str = "loss_",
+                          validate_grid: bool = True):
         metrics = {}
         stage, prefix = raymarched, keys_prefix
         while stage is not None:
             metrics.update(self.view_metrics(
                 image_sampling_grid=xys, images_pred=stage.features, images=image_rgb,
-                depths_pred=stage.depths, depths=depth_map, keys_prefix=prefix,
+                depths_pred=stage.depths, depths=depth_map, keys_prefix=prefix, validate_grid=validate_grid,
             ))
             stage, prefix = stage.prev_stage, prefix + "prev_stage_"
         return metrics

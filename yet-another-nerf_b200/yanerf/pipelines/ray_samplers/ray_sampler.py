@@ -17,8 +17,11 @@ from .builder import RAY_SAMPLERS
 from .utils import EvaluationMode, RayBundle, RenderSamplingMode
 
 
-def _safe_multinomial(input: torch.Tensor, num_samples: int) -> torch.Tensor:
-    """Without replacement where a row has enough non-zero weights, with replacement otherwise."""
+def _safe_multinomial(input: torch.Tensor, num_samples: int, all_positive: bool = False) -> torch.Tensor:
+    """Without replacement where a row has enough non-zero weights, with replacement otherwise.
+    `all_positive`: the caller built `input` as all-ones (no mask), so no device->host check is needed."""
+    if all_positive and input.shape[-1] >= num_samples:
+        return torch.multinomial(input, num_samples, replacement=False)
     enough = (input > 0.0).sum(dim=-1) >= num_samples
     if bool(enough.all()):
         return torch.multinomial(input, num_samples, replacement=False)
@@ -80,6 +83,7 @@ class _RaySampler(torch.nn.Module):
         xy = None
         spatial: Tuple[int, ...] = (H, W)
         if num_rays is not None:
+            plain = mask is None and sampling_prob_mask is None
             if mask is not None:
                 assert tuple(mask.shape) == (B, H, W)
                 weights = mask.reshape(B, -1).float()
@@ -107,7 +111,7 @@ class _RaySampler(torch.nn.Module):
                         f"Invalida `sampling_prob_mask`, shape of {sampling_prob_mask.shape}, want (B, H, W) or (B, L, H, W)"
                     )
             if weights.ndim == 2:
-                rays_idx = _safe_multinomial(weights, num_rays)
+                rays_idx = _safe_multinomial(weights, num_rays, all_positive=plain)
             else:
                 rays_idx = torch.cat([_safe_multinomial(weights[:, i], num_rays[i]) for i in range(len(num_rays))], dim=-1)
             xy = torch.stack((rays_idx % W, rays_idx // W), dim=-1).float()

@@ -48,11 +48,14 @@ def _flat_pixel_index(grid: torch.Tensor, width: int) -> torch.Tensor:
     return (flat[:, :, 0] + width * flat[:, :, 1]).long()
 
 
-def sample_grid(tensor: torch.Tensor, image_sampling_grid: torch.Tensor) -> torch.Tensor:
-    """Gather `tensor` [B,H,W,C] at float pixel coordinates `image_sampling_grid` [B,*sp,2] -> [B,*sp,C]."""
+def sample_grid(tensor: torch.Tensor, image_sampling_grid: torch.Tensor, validate: bool = True) -> torch.Tensor:
+    """Gather `tensor` [B,H,W,C] at float pixel coordinates `image_sampling_grid` [B,*sp,2] -> [B,*sp,C].
+    `validate` keeps the reference's range assertions (two device->host syncs); callers that produced the grid
+    themselves may skip them."""
     B, H, W, C = tensor.shape
-    assert image_sampling_grid[..., 0].max() < W, "Invalid ray_sampler.image_width"
-    assert image_sampling_grid[..., 1].max() < H, "Invalid ray_sampler.image_height"
+    if validate:
+        assert image_sampling_grid[..., 0].max() < W, "Invalid ray_sampler.image_width"
+        assert image_sampling_grid[..., 1].max() < H, "Invalid ray_sampler.image_height"
     idx = _flat_pixel_index(image_sampling_grid, W)[:, :, None].expand(-1, -1, C)
     out = torch.gather(tensor.reshape(B, H * W, C), 1, idx)
     return out.reshape(B, *image_sampling_grid.shape[1:-1], C)
@@ -118,8 +121,8 @@ class ViewMetrics(torch.nn.Module):
     """Per-image (shape `(B,)`) rgb mse / huber (+ optional depth abs error), keys prefixed."""
 
     def forward(self, image_sampling_grid, images=None, images_pred=None, depths=None, depths_pred=None,
-                loss_reweight_masks=None, keys_prefix: Optional[str] = "loss_"):
-        pick = lambda t: None if t is None else sample_grid(t, image_sampling_grid)
+                loss_reweight_masks=None, keys_prefix: Optional[str] = "loss_", validate_grid: bool = True):
+        pick = lambda t: None if t is None else sample_grid(t, image_sampling_grid, validate_grid)
         images, depths, loss_reweight_masks = pick(images), pick(depths), pick(loss_reweight_masks)
         preds = {}
         if images is not None and images_pred is not None:

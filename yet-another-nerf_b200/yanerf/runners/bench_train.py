@@ -68,6 +68,7 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+    trainer.finish()
 
     rays = n_rays * world
     value = rays * args.steps / (total_ms * 1e-3)

@@ -54,6 +54,16 @@ class FusedTrainer:
                 p.grad = self.flat_grad[off:off + k].view_as(p)
                 off += k
         self.step_count = 0
+        self._flag_host, self._flag_event, self._flag_pending = None, None, False
+        # no device->host sync inside the step: pixel-grid range checks move to the host (shapes) and the refiner's
+        # "Negative weights provided." flag is read once, after the whole step has been queued
+        pipeline.validate_pixel_grid = False
+        self._refiners = [m for m in pipeline.modules() if hasattr(m, "check_weights")]
+        for r in getattr(getattr(pipeline, "renderer", None), "_refiners", {}).values():
+            if r not in self._refiners:
+                self._refiners.append(r)
+        for r in self._refiners:
+            r.check_weights = False
         self._mlps = [m for m in pipeline.modules() if hasattr(m, "invalidate_packed_weights")]
         self._broadcast_parameters()
 
@@ -77,7 +87,36 @@ class FusedTrainer:
             raise KeyError("objective")  # runners/apis.py:90-91
         preds["objective"].mean().backward()
         self.optimizer_step(lr)
+        self._deferred_checks()
         return preds
+
+    def _deferred_checks(self) -> None:
+        """The refiner's device flag of step k is copied to pinned memory asynchronously and examined at the end of
+        step k+1 (or by `finish()`), so the host never waits for the GPU inside a step."""
+        self._raise_if_flagged(wait=False)
+        flags = [r.last_flag for r in self._refiners if r.last_flag is not None]
+        if flags:
+            if self._flag_host is None:
+                self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._flag_event = torch.cuda.Event()
+            self._flag_host.copy_(torch.stack([f.reshape(()) for f in flags]).max().reshape(1), non_blocking=True)
+            self._flag_event.record()
+            self._flag_pending = True
+
+    def _raise_if_flagged(self, wait: bool) -> None:
+        if not self._flag_pending:
+            return
+        if wait:
+            self._flag_event.synchronize()
+        elif not self._flag_event.query():
+            return
+        self._flag_pending = False
+        if int(self._flag_host.item()) != 0:
+            raise ValueError("Negative weights provided.")  # renderers/utils.py:123-124
+
+    def finish(self) -> None:
+        """Wait for outstanding work and surface any deferred error."""
+        self._raise_if_flagged(wait=True)
 
     def optimizer_step(self, lr: Optional[float] = None) -> None:
         if self.world > 1:
