@@ -5,11 +5,11 @@
 // points = o + z*d, 63-channel harmonic embedding, the 8x256 skip trunk, density head, intermediate
 // linear, LinearWithRepeat colour hidden layer and the sigmoid colour head, in ONE persistent kernel.
 //
-// One CTA per SM, 320 threads:
+// One CTA per SM, 352 threads:
 //   warp 0      TMA producer: streams 16 KB weight blocks [128 n x 64 k] (pre-swizzled image) through a
 //               4-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128, K=16, fp32 accumulate in
-//               TMEM); A = activation tile in shared memory (K-major, 128B swizzle), B = ring slot.
+//   warps 1,10  MMA issuers, one per tile: an elected thread issues tcgen05.mma (M=128, N=128, K=16, fp32 accumulate
+//               in TMEM); A = the tile's activation blocks in shared memory (K-major, 128B swizzle), B = ring slot.
 //   warps 2-5   epilogue group 0, warps 6-9 epilogue group 1: tcgen05.ld the accumulator, add bias, ReLU,
 //               convert to 16 bit and write the next layer's A operand back to shared memory.  The first
 //               "epilogue" of a tile computes the embedding, the last ones compute the fp32 heads.
@@ -18,6 +18,7 @@
 // the epilogue of half 0 (-> activation blocks 0,1 of the next layer) runs while half 1 is still being multiplied,
 // and the next layer starts on blocks 0,1 while the epilogue of half 1 fills blocks 2,3.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "mlp_common.cuh"
 #include "sm100_ptx.cuh"
@@ -25,7 +26,7 @@
 namespace ynb {
 
 constexpr int kRing = 4;
-constexpr int kFwdThreads = 320;
+constexpr int kFwdThreads = 352;  // warp 0 TMA, warps 1 and 10 MMA issuers (tile 0 / tile 1), warps 2-9 epilogue
 constexpr int kSmemAct = 0;                              // [2][4][16 KB]
 constexpr int kSmemEmb = kSmemAct + 2 * 4 * kBlkBytes;   // [2][16 KB]
 constexpr int kSmemRing = kSmemEmb + 2 * kBlkBytes;      // [4][16 KB]
@@ -46,6 +47,7 @@ struct FwdParams {
   uint8_t* stash;  // nullptr in inference
   int64_t n_points;
   int P;
+  int debug;  // timing experiments only (YN_FWD_DEBUG bit mask): 1 = epilogue skips TMEM/STS work, 2 = producer skips the copies
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -140,9 +142,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
   const uint32_t s_emb = smem_base + kSmemEmb;
   const uint32_t s_ring = smem_base + kSmemRing;
   const uint32_t s_bar = smem_base + kSmemBar;
-  // barriers (8 B each): full[4], empty[4], half_full[2], blk01_free, epi_done[2]; then the TMEM base address
+  // barriers (8 B each): full[4], empty[4], then per tile g: half_full[g][2], blk01_free[g], epi_done[g][2];
+  // then the TMEM base address
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kRing, bar_hfull = s_bar + 16 * kRing,
-                 bar_b01 = bar_hfull + 16, bar_epi = bar_b01 + 8, s_tmem_ptr = bar_epi + 16;
+                 bar_b01 = bar_hfull + 32, bar_epi = bar_b01 + 16, s_tmem_ptr = bar_epi + 32;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,13 +157,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRing; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 2);  // both MMA issuers release a weight block
     }
-    mbar_init(bar_hfull, 1);
-    mbar_init(bar_hfull + 8, 1);
-    mbar_init(bar_b01, 1);
-    mbar_init(bar_epi, 256);
-    mbar_init(bar_epi + 8, 256);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar_hfull + 16 * g, 1);
+      mbar_init(bar_hfull + 16 * g + 8, 1);
+      mbar_init(bar_b01 + 8 * g, 1);
+      mbar_init(bar_epi + 16 * g, 128);
+      mbar_init(bar_epi + 16 * g + 8, 128);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -184,21 +189,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           for (int j = 0; j < per_half * A.nnh(l); ++j, ++s) {
             const uint32_t bytes = (j % per_half) == nkb ? kBiasBlkBytes : kBlkBytes;
             mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-            mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-            bulk_g2s(s_ring + slot * kBlkBytes, p.wpack + (size_t)s * kBlkBytes, bytes, bar_full + 8 * slot);
+            if (p.debug & 2) {
+              mbar_arrive(bar_full + 8 * slot);
+            } else {
+              mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+              bulk_g2s(s_ring + slot * kBlkBytes, p.wpack + (size_t)s * kBlkBytes, bytes, bar_full + 8 * slot);
+            }
             if (++slot == kRing) { slot = 0; phase ^= 1; }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    // Both tiles consume every weight block (one L2 read feeds 8 MMAs).  Dependencies on the epilogue:
-    //   epi_done[0]: output blocks 0,1 of the previous layer written and accumulator half 0 drained
-    //   epi_done[1]: blocks 2,3 written and accumulator half 1 drained
+  } else if (warp == 1 || warp == 10) {
+    // ---------------------------------------------------------------- MMA issuers (one per tile of the pair)
+    // Both issuers consume every weight block (one L2 read feeds both tiles); each owns its tile's accumulators
+    // and barriers.  Dependencies on the tile's epilogue group:
+    //   epi_done[g][0]: output blocks 0,1 of the previous layer written and accumulator half 0 drained
+    //   epi_done[g][1]: blocks 2,3 written and accumulator half 1 drained
+    const int g = warp == 1 ? 0 : 1;
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(128, 128, kFmt, 0, 0);
+      const uint32_t my_epi = bar_epi + 16 * g, my_hfull = bar_hfull + 16 * g, my_b01 = bar_b01 + 8 * g;
+      const uint32_t act_base = s_act + g * 4 * kBlkBytes, emb_base = s_emb + g * kBlkBytes;
       uint32_t slot = 0, phase = 0;
       uint32_t ed_phase0 = 0, ed_phase1 = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -208,60 +221,54 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           const int nnh = A.nnh(l);
           const int kb_free = nkb > 1 ? 1 : 0;
           const bool has_bias = A.has_bias_stage(l);
-          mbar_wait(bar_epi, ed_phase0);
+          mbar_wait(my_epi, ed_phase0);
           ed_phase0 ^= 1;
           tc_fence_after();
           bool waited1 = false;
           for (int nh = 0; nh < nnh; ++nh) {
+            const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
             for (int kb = 0; kb < nkb; ++kb) {
               if (!waited1 && (nh == 1 || (kb >= 2 && kb < nkbh))) {
-                mbar_wait(bar_epi + 8, ed_phase1);
+                mbar_wait(my_epi + 8, ed_phase1);
                 ed_phase1 ^= 1;
                 tc_fence_after();
                 waited1 = true;
               }
               mbar_wait(bar_full + 8 * slot, phase);
               tc_fence_after();
-              const uint32_t b_base = s_ring + slot * kBlkBytes;
+              const uint64_t b_desc = umma_desc_kmajor(s_ring + slot * kBlkBytes);
+              const uint64_t a_desc = umma_desc_kmajor((kb < nkbh) ? (act_base + kb * kBlkBytes) : emb_base);
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const uint32_t a_base = (kb < nkbh) ? (s_act + (g * 4 + kb) * kBlkBytes) : (s_emb + g * kBlkBytes);
-                const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16(d_tmem, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
-                           (kb | k) != 0);
-              }
+              for (int k = 0; k < 4; ++k)  // K advances by 32 bytes = 2 descriptor units inside the swizzle atom
+                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
               umma_commit(bar_empty + 8 * slot);
               if (++slot == kRing) { slot = 0; phase ^= 1; }
               // activation blocks 0,1 are not read again in this layer after (last half, kb_free)
-              if (nh == nnh - 1 && kb == kb_free) umma_commit(bar_b01);
+              if (nh == nnh - 1 && kb == kb_free) umma_commit(my_b01);
             }
             if (has_bias) {
               // + bias: embedding slice 3 (channel 63 == 1) x the [128 x 16] bias block
               mbar_wait(bar_full + 8 * slot, phase);
               tc_fence_after();
-              const uint64_t b_desc = umma_desc_kmajor_k16_nosw(s_ring + slot * kBlkBytes);
-#pragma unroll
-              for (int g = 0; g < 2; ++g)
-                umma_f16(tmem_base + g * 256 + nh * 128, umma_desc_kmajor(s_emb + g * kBlkBytes + 96), b_desc, idesc, 1);
+              umma_f16(d_tmem, umma_desc_kmajor(emb_base + 96), umma_desc_kmajor_k16_nosw(s_ring + slot * kBlkBytes), idesc, 1);
               umma_commit(bar_empty + 8 * slot);
               if (++slot == kRing) { slot = 0; phase ^= 1; }
             }
-            umma_commit(bar_hfull + 8 * nh);
+            umma_commit(my_hfull + 8 * nh);
           }
           if (!waited1) {
-            mbar_wait(bar_epi + 8, ed_phase1);
+            mbar_wait(my_epi + 8, ed_phase1);
             ed_phase1 ^= 1;
           }
         }
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ---------------------------------------------------------------- epilogue groups
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t my_epi = bar_epi + 16 * g, my_hfull = bar_hfull + 16 * g, my_b01 = bar_b01 + 8 * g;
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
     const uint32_t act_g = s_act + g * 4 * kBlkBytes;
@@ -312,8 +319,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       // the embedding acts as the epilogue of a virtual layer -1: both halves "done"
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_epi);
-      mbar_arrive(bar_epi + 8);
+      mbar_arrive(my_epi);
+      mbar_arrive(my_epi + 8);
       if (kStash) {
         named_bar_sync(1 + g, 128);
         if (stash_leader && tile_live) {
@@ -332,16 +339,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         const float* wd = p.aux + A.aux_wd();
         const float* w2 = p.aux + A.aux_w2();
         // ---- half 0: accumulator columns [0,128) -> activation blocks 0,1
-        mbar_wait(bar_hfull, hf_phase0);
+        mbar_wait(my_hfull, hf_phase0);
         hf_phase0 ^= 1;
-        mbar_wait(bar_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
+        mbar_wait(my_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
         b01_phase ^= 1;
         tc_fence_after();
         if (kStash) {
           if (stash_leader) bulk_wait_read<0>();  // the previous layer's stash store has read the buffer
           named_bar_sync(1 + g, 128);
         }
-        if (is_color)
+        if (p.debug & 1) {
+        } else if (is_color)
           epilogue_half<kFmt, 2, kStash>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
         else if (is_inter)
           epilogue_half<kFmt, 1, true>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
@@ -350,20 +358,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         tc_fence_before();
         fence_proxy_async_smem();
         // the last layer feeds no MMA: the next pair's embedding arrival (program order) covers the TMEM hand-over
-        if (!is_color) mbar_arrive(bar_epi);
+        if (!is_color) mbar_arrive(my_epi);
         // ---- half 1: columns [128,256) -> blocks 2,3 (the colour hidden layer is 128 wide: nothing to do)
         if (!is_color) {
-          mbar_wait(bar_hfull + 8, hf_phase1);
+          mbar_wait(my_hfull + 8, hf_phase1);
           hf_phase1 ^= 1;
           tc_fence_after();
-          if (is_inter)
+          if (p.debug & 1) {
+          } else if (is_inter)
             epilogue_half<kFmt, 1, true>(t_row, 128, bias, wd, false, dens, w2, acc, act_row, swz);
           else
             epilogue_half<kFmt, 0, true>(t_row, 128, bias, wd, is_last_trunk, dens, w2, acc, act_row, swz);
           tc_fence_before();
           fence_proxy_async_smem();
         }
-        if (!is_color) mbar_arrive(bar_epi + 8);
+        if (!is_color) mbar_arrive(my_epi + 8);
         if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
         if (is_color && valid) {
           const int C = A.color_dim;
@@ -435,5 +444,9 @@ extern "C" int yn_mlp_fwd(const yn_mlp_arch* arch, const float* origins, const f
   p.stash = static_cast<uint8_t*>(stash);
   p.n_points = R * P;
   p.P = P;
+  {
+    const char* dbg = getenv("YN_FWD_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   return ynb::launch_fwd(p, static_cast<cudaStream_t>(stream));
 }
