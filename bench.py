@@ -299,10 +299,25 @@ def _main():
     achieved = flops_fine / (fine_ms * 1e-3) / 1e12
     step_ms = total_ms / args.steps
     kernel_ms = {k: round(v[1] / args.steps, 3) for k, v in prof.items()}
+    traffic = None
+    prof_path = os.path.join(REPO, "profiles", "mlp_fwd_r01_ncu_full.json")
+    if os.path.exists(prof_path):  # dram__bytes_read.sum + dram__bytes_write.sum of the fine-pass launch (ncu --set full)
+        try:
+            fine_launch = json.load(open(prof_path))["launches"][1]
+
+            def _bytes(txt):
+                v, unit = txt.split()
+                return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+
+            traffic = _bytes(fine_launch["dram__bytes_read.sum"]) + _bytes(fine_launch["dram__bytes_write.sum"])
+        except Exception:
+            traffic = None
     roofline = {"bound": "tensor", "kernel": "mlp_fwd_kernel (fine pass, 192 points/ray)", "achieved": round(achieved, 1),
                 "peak": peaks["tensor"], "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "unit": "TFLOP/s", "frac": round(achieved / peaks["tensor"], 4), "traffic": None,
-                "launch_ms": round(fine_ms, 3), "coarse_launch_ms": round(sum(coarse) / len(coarse), 3),
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tensor"], 4), "traffic": traffic,
+                "traffic_note": "DRAM bytes of one fine-pass launch from profiles/mlp_fwd_r01_ncu_full.json; algorithmic "
+                                "HBM bytes are 20 B/point = 2.46e9",
+                "flops_per_launch": flops_fine, "launch_ms": round(fine_ms, 3), "coarse_launch_ms": round(sum(coarse) / len(coarse), 3),
                 "share_of_step": round((sum(fine) + sum(coarse)) / total_ms, 4), "kernel_ms_per_step": kernel_ms}
 
     line = None

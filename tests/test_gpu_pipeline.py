@@ -244,3 +244,32 @@ def test_fused_trainer_converges_like_reference_runner():
     last = float(ev["objective"].mean())
     print("objective", first, "->", last)
     assert last < 0.01 and last < first
+
+
+def test_fern_shape_llff_depth_tensors_and_custom_rays():
+    """BASELINE configs[3]: fern.yml shape (378x504, 64+64 samples, 1024 rays) with per-image min/max depth TENSORS
+    (reduced with .mean().item() like ray_sampler.py:280-283; there is no NDC warp in the reference)."""
+    B, H, W = 2, 378, 504
+    pipe = build_pipeline(H, W, 1024, 64, 0.0, 131072, min_depth=0.1, max_depth=8.0).to(DEV)
+    load_synth_nets(pipe, seeds=(5, 6), gain=1.0)
+    poses, focal = syn.synth_camera(B, seed=7).to(DEV), torch.full((B, 1), syn.FERN_FOCAL, device=DEV)
+    near, far = torch.tensor([[1.2], [1.4]], device=DEV), torch.tensor([[12.0], [11.0]], device=DEV)
+    image = syn.synth_image(B, H, W, seed=8).to(DEV)
+    out = pipe(poses=poses, focal_lengths=focal, image_rgb=image, min_depth=near, max_depth=far,
+               evaluation_mode=EvaluationMode.TRAINING)
+    assert out["objective"].shape == (B,) and out["rendered_images"].shape == (B, H, W, 3)
+    out["objective"].mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in pipe.parameters())
+    with torch.no_grad():
+        ev = pipe(poses=poses[:1], focal_lengths=focal[:1], image_rgb=image[:1], min_depth=near[:1], max_depth=far[:1],
+                  evaluation_mode=EvaluationMode.EVALUATION)
+    assert ev["rendered_images"].shape == (1, H, W, 3) and torch.isfinite(ev["rendered_images"]).all()
+    d = ev["rendered_depths"]
+    assert float(d.min()) >= 1.2 - 1e-3 and float(d.max()) <= 12.0 + 1e-3
+    # oracle on a slab of rays of the same image (chunk plan of fern: 94 x 2027 rays)
+    spec = oracle_spec(H, W, 64, 0.0, 131072, min_depth=1.2, max_depth=12.0)
+    nets = [{k: v.detach().cpu() for k, v in fn._fn.state_dict().items()} for fn in pipe.implicit_functions]
+    s, e = 90000, 90000 + 2027
+    ref = O.render_image(nets, spec, poses[:1].cpu(), focal[:1].cpu(), ray_slice=(s, e))
+    got = ev["rendered_images"].reshape(1, H * W, 3)[:, s:e].cpu()
+    assert float((got - ref["features"]).abs().max()) <= 2e-3

@@ -279,6 +279,39 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     const int nfx = A.n_freq_xyz;
     const int blocks_per_tile = A.stash_blocks_per_tile();
     uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0;
+    int l_emb_last = 0;  // last layer that reads the embedding block as an operand
+    for (int l = 1; l < A.n_layers; ++l)
+      if (A.has_emb(l)) l_emb_last = l;
+
+    // harmonic embedding (models/utils.py:90-103) of row `row` of tile `t` -> this tile's embedding block:
+    // [sin(x f_k) | cos(x f_k) | x], channel a*L+k, channel 63 = 1 (bias).  (A double-angle recurrence from the base
+    // octave was tried: its error triples per octave, 8e-4 at 2^9, visible against the fp16 operand ulp -- rejected.)
+    auto write_embedding = [&](int64_t t) {
+      const int64_t gi = t * kTileM + row;
+      const bool ok = gi < p.n_points;
+      float pt[3] = {0.f, 0.f, 0.f};
+      if (ok) {
+        const int64_t r = gi / p.P;
+        const float z = __ldg(p.lengths + gi);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          pt[a] = __fadd_rn(__ldg(p.origins + r * 3 + a), __fmul_rn(z, __ldg(p.directions + r * 3 + a)));
+      }
+      for (int a = 0; a < 3; ++a) {
+        float f = 1.f;
+        for (int k = 0; k < nfx; ++k, f *= 2.f) {
+          float sn, cs;
+          sincosf(pt[a] * f, &sn, &cs);  // full-accuracy range reduction: arguments reach 2^9 * 6 rad
+          if (!ok) { sn = 0.f; cs = 0.f; }
+          const int ch = a * nfx + k;
+          st_shared_u16(emb_g + sw128_offset(row, ch), to_half_bits<kFmt>(sn));
+          st_shared_u16(emb_g + sw128_offset(row, 3 * nfx + ch), to_half_bits<kFmt>(cs));
+        }
+        st_shared_u16(emb_g + sw128_offset(row, 6 * nfx + a), to_half_bits<kFmt>(pt[a]));
+      }
+      for (int ch = 6 * nfx + 3; ch < 63; ++ch) st_shared_u16(emb_g + sw128_offset(row, ch), 0);
+      st_shared_u16(emb_g + sw128_offset(row, 63), to_half_bits<kFmt>(1.f));
+    };
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
@@ -292,30 +325,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         if (stash_leader) bulk_wait_read<0>();
         named_bar_sync(1 + g, 128);
       }
-      // ---- embedding (models/utils.py:90-103): [sin(x f_k) | cos(x f_k) | x], channel a*L+k
-      {
-        float pt[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-          const float z = __ldg(p.lengths + gidx);
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-            pt[a] = __fadd_rn(__ldg(p.origins + ray * 3 + a), __fmul_rn(z, __ldg(p.directions + ray * 3 + a)));
-        }
-        for (int a = 0; a < 3; ++a) {
-          float f = 1.f;
-          for (int k = 0; k < nfx; ++k, f *= 2.f) {
-            float s, c;
-            sincosf(pt[a] * f, &s, &c);
-            if (!valid) { s = 0.f; c = 0.f; }
-            const int ch = a * nfx + k;
-            st_shared_u16(emb_g + sw128_offset(row, ch), to_half_bits<kFmt>(s));
-            st_shared_u16(emb_g + sw128_offset(row, 3 * nfx + ch), to_half_bits<kFmt>(c));
-          }
-          st_shared_u16(emb_g + sw128_offset(row, 6 * nfx + a), to_half_bits<kFmt>(pt[a]));
-        }
-        for (int ch = 6 * nfx + 3; ch < 63; ++ch) st_shared_u16(emb_g + sw128_offset(row, ch), 0);
-        st_shared_u16(emb_g + sw128_offset(row, 63), to_half_bits<kFmt>(1.f));  // bias channel
-      }
+      // ---- embedding of this tile: computed here for the CTA's first pair, otherwise prefetched during the
+      // previous pair (see below)
+      if (pair == (int64_t)blockIdx.x) write_embedding(tile);
       // the embedding acts as the epilogue of a virtual layer -1: both halves "done"
       tc_fence_before();
       fence_proxy_async_smem();
@@ -373,6 +385,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           fence_proxy_async_smem();
         }
         if (!is_color) mbar_arrive(my_epi + 8);
+        if (l == l_emb_last && pair + gridDim.x < n_pairs) {
+          // every MMA that reads this tile's embedding as an operand has completed (half_full[1] of this layer):
+          // prefetch the next pair's embedding now, in the shadow of the remaining layers.  Later bias MMAs read
+          // only channels 48..63 of it against zero weights (and the constant 1 of channel 63 is rewritten as 1).
+          if (kStash) {
+            if (stash_leader) bulk_wait_read<0>();
+            named_bar_sync(1 + g, 128);
+          }
+          write_embedding(2 * (pair + gridDim.x) + g);
+        }
         if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
         if (is_color && valid) {
           const int C = A.color_dim;
