@@ -21,7 +21,7 @@
 namespace ynb {
 
 constexpr int kBwdRing = 4;
-constexpr int kBwdThreads = 320;
+constexpr int kBwdThreads = 352;  // warp 0 TMA, warps 1 and 10 MMA issuers (tile 0 / 1), warps 2-9 epilogue
 constexpr int kBSmemG = 0;                                  // [2][4][16 KB] dY tiles
 constexpr int kBSmemRing = kBSmemG + 2 * 4 * kBlkBytes;     // [4][16 KB]
 constexpr int kBSmemBar = kBSmemRing + kBwdRing * kBlkBytes;
@@ -124,8 +124,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
   const uint32_t s_g = smem_base + kBSmemG;
   const uint32_t s_ring = smem_base + kBSmemRing;
   const uint32_t s_bar = smem_base + kBSmemBar;
+  // barriers: full[4], empty[4], then per tile g: half_full[g][2], blk01_free[g], epi_done[g][2]
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kBwdRing, bar_hfull = s_bar + 16 * kBwdRing,
-                 bar_b01 = bar_hfull + 16, bar_epi = bar_b01 + 8, s_tmem_ptr = bar_epi + 16;
+                 bar_b01 = bar_hfull + 32, bar_epi = bar_b01 + 16, s_tmem_ptr = bar_epi + 32;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,13 +140,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBwdRing; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 2);  // both MMA issuers release a weight block
     }
-    mbar_init(bar_hfull, 1);
-    mbar_init(bar_hfull + 8, 1);
-    mbar_init(bar_b01, 1);
-    mbar_init(bar_epi, 256);
-    mbar_init(bar_epi + 8, 256);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar_hfull + 16 * g, 1);
+      mbar_init(bar_hfull + 16 * g + 8, 1);
+      mbar_init(bar_b01 + 8 * g, 1);
+      mbar_init(bar_epi + 16 * g, 128);
+      mbar_init(bar_epi + 16 * g + 8, 128);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -175,52 +178,51 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || warp == 10) {
+    // ---------------------------------------------------------------- MMA issuers (one per tile of the pair)
+    const int g = warp == 1 ? 0 : 1;
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(128, 128, kFmt, 0, 0);
+      const uint32_t my_epi = bar_epi + 16 * g, my_hfull = bar_hfull + 16 * g, my_b01 = bar_b01 + 8 * g;
+      const uint32_t g_base = s_g + g * 4 * kBlkBytes;
       uint32_t slot = 0, phase = 0, ed_phase0 = 0, ed_phase1 = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int st = 0; st < n_steps; ++st) {
           const int nkb = st == 0 ? 2 : 4;  // reduction over the layer's outputs (128 for the colour hidden layer)
-          mbar_wait(bar_epi, ed_phase0);
+          mbar_wait(my_epi, ed_phase0);
           ed_phase0 ^= 1;
           tc_fence_after();
           bool waited1 = false;
           for (int nh = 0; nh < 2; ++nh) {
+            const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
             for (int kb = 0; kb < nkb; ++kb) {
               if (!waited1 && (nh == 1 || kb >= 2)) {
-                mbar_wait(bar_epi + 8, ed_phase1);
+                mbar_wait(my_epi + 8, ed_phase1);
                 ed_phase1 ^= 1;
                 tc_fence_after();
                 waited1 = true;
               }
               mbar_wait(bar_full + 8 * slot, phase);
               tc_fence_after();
-              const uint32_t b_base = s_ring + slot * kBlkBytes;
+              const uint64_t b_desc = umma_desc_kmajor(s_ring + slot * kBlkBytes);
+              const uint64_t a_desc = umma_desc_kmajor(g_base + kb * kBlkBytes);
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const uint32_t a_base = s_g + (g * 4 + kb) * kBlkBytes;
-                const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16(d_tmem, umma_desc_kmajor(a_base + k * 32), umma_desc_kmajor(b_base + k * 32), idesc,
-                           (kb | k) != 0);
-              }
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
               umma_commit(bar_empty + 8 * slot);
               if (++slot == kBwdRing) { slot = 0; phase ^= 1; }
-              if (nh == 1 && kb == 1) umma_commit(bar_b01);
+              if (nh == 1 && kb == 1) umma_commit(my_b01);
             }
-            umma_commit(bar_hfull + 8 * nh);
+            umma_commit(my_hfull + 8 * nh);
           }
         }
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ---------------------------------------------------------------- epilogue groups
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;
+    const uint32_t my_epi = bar_epi + 16 * g, my_hfull = bar_hfull + 16 * g, my_b01 = bar_b01 + 8 * g;
     const int row = q * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
     const uint32_t g_g = s_g + g * 4 * kBlkBytes;
@@ -280,8 +282,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(bar_epi);
-      mbar_arrive(bar_epi + 8);
+      mbar_arrive(my_epi);
+      mbar_arrive(my_epi + 8);
       bwd_named_bar_sync(1 + g, 128);
       if (leader && tile_live) {
         uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
@@ -296,9 +298,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         const bool last = st == n_steps - 1;
         const uint8_t* mask_row = stash_row + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
         // ---- half 0
-        mbar_wait(bar_hfull, hf_phase0);
+        mbar_wait(my_hfull, hf_phase0);
         hf_phase0 ^= 1;
-        mbar_wait(bar_b01, b01_phase);
+        mbar_wait(my_b01, b01_phase);
         b01_phase ^= 1;
         tc_fence_after();
         if (leader) bulk_wait_read<0>();
@@ -308,9 +310,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mask_row, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
-        if (!last) mbar_arrive(bar_epi);
+        if (!last) mbar_arrive(my_epi);
         // ---- half 1
-        mbar_wait(bar_hfull + 8, hf_phase1);
+        mbar_wait(my_hfull + 8, hf_phase1);
         hf_phase1 ^= 1;
         tc_fence_after();
         if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mask_row, swz, dd, wd, g_row);
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mask_row, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
-        if (!last) mbar_arrive(bar_epi + 8);
+        if (!last) mbar_arrive(my_epi + 8);
         bwd_named_bar_sync(1 + g, 128);
         if (leader && tile_live) {
           uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
