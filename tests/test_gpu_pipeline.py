@@ -273,3 +273,44 @@ def test_fern_shape_llff_depth_tensors_and_custom_rays():
     ref = O.render_image(nets, spec, poses[:1].cpu(), focal[:1].cpu(), ray_slice=(s, e))
     got = ev["rendered_images"].reshape(1, H * W, 3)[:, s:e].cpu()
     assert float((got - ref["features"]).abs().max()) <= 2e-3
+
+
+def test_full_size_render_properties():
+    """BASELINE configs[1] at full size (800x800, 64+128): size-independent properties instead of an oracle run.
+    determinism (bitwise), sorted refined depths, weights in [0,1] summing to opacity, linearity of the colour
+    compositing in rgb, chunk-invariance on a row band."""
+    from yanerf import ops
+
+    H = W = 800
+    pipe = build_pipeline(H, W, 4096, 128, 0.2, 131072).to(DEV)
+    load_synth_nets(pipe, seeds=(0, 1), gain=1.0)
+    poses, focal = syn.synth_camera(1, seed=0, jitter=0.0).to(DEV), torch.full((1, 1), syn.LEGO_FOCAL, device=DEV)
+    with torch.no_grad():
+        a = pipe(poses=poses, focal_lengths=focal, evaluation_mode=EvaluationMode.EVALUATION)
+        b = pipe(poses=poses, focal_lengths=focal, evaluation_mode=EvaluationMode.EVALUATION)
+    for k in ("rendered_images", "rendered_depths", "rendered_alpha_masks"):
+        assert torch.equal(a[k], b[k]), f"{k} not deterministic"
+        assert torch.isfinite(a[k]).all()
+    assert a["rendered_images"].shape == (1, H, W, 3)
+    assert float(a["rendered_alpha_masks"].min()) == 1.0  # background_opacity 1e10 saturates every ray (SURVEY 0.10)
+    assert float(a["rendered_depths"].min()) >= 2.0 - 1e-4 and float(a["rendered_depths"].max()) <= 6.0 + 1e-4
+    # renderer-level properties on one band of rays
+    bundle = pipe.ray_sampler(poses, focal, EvaluationMode.EVALUATION)
+    sl = slice(300, 310)
+    o, d, z, xy = (t[:, sl].contiguous() for t in bundle)
+    with torch.no_grad():
+        out = pipe.renderer(o, d, z, xy, None, implicit_functions=pipe.implicit_functions,
+                            evaluation_mode=EvaluationMode.EVALUATION)
+    assert torch.equal(out.features, a["rendered_images"][:, sl]), "band render differs from the full-image render"
+    w = out.aux["weights"]
+    assert w.shape[-1] == 192 and float(w.min()) >= 0.0
+    torch.testing.assert_close(w.sum(-1, keepdim=True), out.alpha_masks, rtol=0, atol=2e-5)
+    zf = ops.sample_pdf_merge(z.reshape(-1, 64), out.prev_stage.aux["weights"].reshape(-1, 64), 128, None)[0]
+    assert bool((zf[:, 1:] >= zf[:, :-1]).all()), "refined depths not ascending"
+    # linearity of compositing in the colours
+    R = zf.shape[0]
+    sig, c1, c2 = torch.randn(R, 192, device=DEV), torch.rand(R, 192, 3, device=DEV), torch.rand(R, 192, 3, device=DEV)
+    cfg = ops.march_cfg(1e10, 1e-6, 0.0, False, False, (0.0, 0.0, 0.0))
+    dd = d.reshape(-1, 3)
+    f1, f2, f12 = (ops.composite(sig, c, zf, dd, cfg)[0] for c in (c1, c2, 2 * c1 + 3 * c2))
+    torch.testing.assert_close(f12, 2 * f1 + 3 * f2, rtol=1e-5, atol=1e-5)
