@@ -155,9 +155,12 @@ class MlpFunction(torch.autograd.Function):
     (the reference never differentiates w.r.t. the rays); the flat parameter vector does."""
 
     @staticmethod
-    def forward(ctx, flat_params, origins, directions, lengths, plan: MlpPlan, need_grad: bool):
-        # NB: grad mode is off inside Function.forward, so the caller decides whether to keep the stash
+    def forward(ctx, flat_params, origins, directions, lengths, plan: MlpPlan, need_grad: bool, grad_out=None):
+        # NB: grad mode is off inside Function.forward, so the caller decides whether to keep the stash.
+        # grad_out: optional flat fp32 buffer the backward kernels accumulate into directly (FusedTrainer's flat
+        # gradient); the autograd gradient of flat_params is then None.
         R, P = lengths.shape
+        ctx.grad_out = grad_out
         stash = None
         if need_grad and R > 0:
             nbytes = N.lib().yn_mlp_stash_bytes(ctypes.byref(plan.arch), R * P)
@@ -174,7 +177,8 @@ class MlpFunction(torch.autograd.Function):
         flat_params, directions, rgb = ctx.saved_tensors
         plan: MlpPlan = ctx.plan
         R, P = ctx.shape
-        grads = torch.zeros_like(flat_params)
+        direct = ctx.grad_out is not None
+        grads = ctx.grad_out if direct else torch.zeros_like(flat_params)
         if R > 0:
             L = N.lib()
             d_density = N.f32c(d_density) if d_density is not None else torch.zeros(R, P, device=rgb.device)
@@ -187,7 +191,7 @@ class MlpFunction(torch.autograd.Function):
                     N.ptr(work, torch.uint8), N.ptr(grads), R, P, N.stream_ptr(),
                 )
         ctx.stash = None
-        return grads, None, None, None, None, None
+        return (None if direct else grads), None, None, None, None, None, None
 
 
 # --------------------------------------------------------------------------- #

@@ -133,6 +133,8 @@ class NeRFMLP(torch.nn.Module):
                              n_hidden_neurons_xyz, n_hidden_neurons_dir, color_dim)
         self._fmt = {False: _default_fmt(False), True: _default_fmt(True)}  # keyed by "needs grad"
         self._plans = {}  # fmt -> [MlpPlan, packed key]
+        self._flat_leaf: Optional[torch.Tensor] = None  # set by FusedTrainer: parameters live in one flat buffer
+        self._flat_grad: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ parameter plumbing
     def ordered_parameters(self) -> List[torch.nn.Parameter]:
@@ -153,6 +155,20 @@ class NeRFMLP(torch.nn.Module):
 
     def _flat(self) -> torch.Tensor:
         return torch.cat([p.reshape(-1) for p in self.ordered_parameters()])
+
+    def use_flat_parameters(self, flat_leaf: Optional[torch.Tensor], flat_grad: Optional[torch.Tensor]) -> None:
+        """The module's parameters are (already) consecutive views of `flat_leaf`'s storage: use it as the autograd
+        leaf and let the backward kernels accumulate straight into `flat_grad` (no per-tensor cat / split / add)."""
+        if flat_leaf is not None:
+            ps = self.ordered_parameters()
+            ptr = flat_leaf.data_ptr()
+            for p in ps:
+                if p.data_ptr() != ptr:
+                    raise ValueError("parameters are not consecutive views of the flat buffer")
+                ptr += p.numel() * 4
+            assert flat_grad is not None and flat_grad.numel() == flat_leaf.numel()
+        self._flat_leaf, self._flat_grad = flat_leaf, flat_grad
+        self.invalidate_packed_weights()
 
     def plan_for(self, flat: torch.Tensor, needs_grad: bool) -> ops.MlpPlan:
         """(Re)pack the tensor-core weight image when the parameters changed since the last call."""
@@ -182,13 +198,14 @@ class NeRFMLP(torch.nn.Module):
             raise ValueError("The shape of global codes is imcompible with the input dim of the network.")
         lead = lengths.shape[:-1]
         P = lengths.shape[-1]
-        flat = self._flat()
+        flat = self._flat_leaf if self._flat_leaf is not None else self._flat()
         need_grad = torch.is_grad_enabled() and flat.requires_grad
         plan = self.plan_for(flat, need_grad)
         o = N.f32c(origins.expand(*lead, 3)).reshape(-1, 3)
         d = N.f32c(directions.expand(*lead, 3)).reshape(-1, 3)
         z = N.f32c(lengths).reshape(-1, P)
-        density, rgb = ops.MlpFunction.apply(flat, o, d, z, plan, need_grad)
+        density, rgb = ops.MlpFunction.apply(flat, o, d, z, plan, need_grad,
+                                             self._flat_grad if self._flat_leaf is not None else None)
         return dict(
             rays_densities=density.reshape(*lead, P, 1),
             rays_features=rgb.reshape(*lead, P, self.color_dim),

@@ -65,6 +65,17 @@ class FusedTrainer:
         for r in self._refiners:
             r.check_weights = False
         self._mlps = [m for m in pipeline.modules() if hasattr(m, "invalidate_packed_weights")]
+        # hand every NeRFMLP its slice of the flat buffers: one autograd leaf per network, gradients accumulated by
+        # the kernels directly into flat_grad
+        offsets = {}
+        off = 0
+        for p in self.params:
+            offsets[id(p)] = off
+            off += p.numel()
+        for m in self._mlps:
+            ps = m.ordered_parameters()
+            o0, k = offsets[id(ps[0])], sum(p.numel() for p in ps)
+            m.use_flat_parameters(self.flat[o0:o0 + k].detach().requires_grad_(True), self.flat_grad[o0:o0 + k])
         self._broadcast_parameters()
 
     def _broadcast_parameters(self) -> None:
