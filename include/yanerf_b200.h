@@ -54,7 +54,7 @@ int yn_ray_bundle(const float* poses, int64_t pose_batch_stride, int64_t pose_ro
  * NeRF MLP (yanerf/pipelines/models/nerf_mlp.py:12-289, models/utils.py:17-245).
  * Architecture family: inner trunk width 256 (the reference never forwards hidden_dim, nerf_mlp.py:88-95),
  * n_layers <= 12, skips anywhere but layer 0, 3*(2*n_freq_xyz+1) <= 64, hidden_last <= 256,
- * hidden_dir <= 128, color_dim <= 4, latent_dim == 0.
+ * hidden_dir <= 128, color_dim <= 3, 3*(2*n_freq_dir+1) <= 32, latent_dim == 0.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct yn_mlp_arch {
   int32_t n_layers;    /* trunk layers (lego: 8) */

@@ -36,7 +36,7 @@ int check_arch(const yn_mlp_arch* a) {
     return fail(YN_ERR_UNSUPPORTED, "direction embedding wider than 32 channels (n_harmonic_functions_dir > 4)");
   if (a->hidden_last < 1 || a->hidden_last > kInner) return fail(YN_ERR_UNSUPPORTED, "n_hidden_neurons_xyz must be in [1,256]");
   if (a->hidden_dir < 1 || a->hidden_dir > kDirPad) return fail(YN_ERR_UNSUPPORTED, "n_hidden_neurons_dir must be in [1,128]");
-  if (a->color_dim < 1 || a->color_dim > 4) return fail(YN_ERR_UNSUPPORTED, "color_dim must be in [1,4]");
+  if (a->color_dim < 1 || a->color_dim > 3) return fail(YN_ERR_UNSUPPORTED, "color_dim must be in [1,3]");
   if (a->fmt != 0 && a->fmt != 1) return fail(YN_ERR_INVALID_ARGUMENT, "fmt must be 0 (fp16) or 1 (bf16)");
   return YN_OK;
 }

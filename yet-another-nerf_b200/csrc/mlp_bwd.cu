@@ -507,24 +507,36 @@ __device__ __forceinline__ float half_bits_to_float(uint16_t bits) {
   return __half2float(*reinterpret_cast<const __half*>(&bits));
 }
 
-// thread j owns feature column j: dwd[j] += sum_r dd[r] * feat[r][j]; dW2[c][j] += sum_r ds[r][c] * hid[r][j].
-// Loads of 8 rows are issued before their FMAs so that 16 requests per thread are in flight.
+// Density head (N = 1) and colour output layer (N = color_dim) weight gradients:
+//   dwd[j] += sum_r dd[r] * feat[r][j],  dW2[c][j] += sum_r ds[r][c] * hid[r][j]   (+ the two bias gradients)
+// Thread (rg, u) of a 256-thread block owns the u-th 16-byte unit (8 columns) of the 512-byte activation row and the
+// rows rg, rg+8, ... of every tile: a warp reads whole rows (4 x 128-byte lines), all loads of a tile are in flight
+// together; the 8 row groups are folded through shared memory once, at the end.
 template <int kFmt>
 __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
   __shared__ float s_dd[kTileM];
   __shared__ float s_ds[kTileM][4];
+  __shared__ float s_red[8][kInner + 3 * kDirPad];
   const Arch& A = p.arch;
   const int n = A.n_layers, C = A.color_dim;
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int blocks_per_tile = A.stash_blocks_per_tile();
-  const int j = threadIdx.x;  // feature column
-  const size_t col_off = (size_t)(j >> 6) * kBlkBytes + ((j & 7) << 1);
-  const uint32_t unit = (j >> 3) & 7;
-  float acc_wd = 0.f, acc_w2[4] = {0.f, 0.f, 0.f, 0.f}, acc_bd = 0.f, acc_b2 = 0.f;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  const int t = threadIdx.x;
+  const int rg = t >> 5, u = t & 31;          // row group, 16-byte unit of the row (columns 8u .. 8u+7)
+  const size_t unit_off = (size_t)(u >> 3) * kBlkBytes;
+  const uint32_t u_in_blk = u & 7;
+  const bool do_hid = u < kDirPad / 8;
+  float acc_wd[8], acc_w2[3][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc_wd[i] = 0.f;
+    acc_w2[0][i] = acc_w2[1][i] = acc_w2[2][i] = 0.f;
+  }
+  float acc_bd = 0.f, acc_b2 = 0.f;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
-    if (j < kTileM) {
-      const int64_t gidx = t * kTileM + j;
+    if (t < kTileM) {
+      const int64_t gidx = tile * kTileM + t;
       float dd = 0.f, ds[4] = {0.f, 0.f, 0.f, 0.f};
       if (gidx < p.n_points) {
         dd = p.d_density[gidx];
@@ -533,43 +545,64 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
           ds[c] = p.d_rgb[gidx * C + c] * y * (1.f - y);
         }
       }
-      s_dd[j] = dd;
-      for (int c = 0; c < 4; ++c) s_ds[j][c] = ds[c];
+      s_dd[t] = dd;
+      for (int c = 0; c < 4; ++c) s_ds[t][c] = ds[c];
     }
     __syncthreads();
-    const uint8_t* tile = p.stash + (size_t)t * blocks_per_tile * kBlkBytes;
-    const uint8_t* feat = tile + (size_t)A.stash_block_of_layer(n - 1) * kBlkBytes + col_off;  // last trunk output
-    const uint8_t* hid = tile + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes + col_off;   // colour hidden
-    const bool do_hid = j < kDirPad;
-#pragma unroll 1
-    for (int r0 = 0; r0 < kTileM; r0 += 8) {
-      uint16_t f[8], h[8];
+    const uint8_t* base = p.stash + (size_t)tile * blocks_per_tile * kBlkBytes;
+    const uint8_t* feat = base + (size_t)A.stash_block_of_layer(n - 1) * kBlkBytes + unit_off;  // last trunk output
+    const uint8_t* hid = base + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes + unit_off;   // colour hidden
+    uint4 f[16], h[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + i;
-        const size_t off = (size_t)r * 128 + ((unit ^ (uint32_t)(r & 7)) << 4);
-        f[i] = __ldg(reinterpret_cast<const uint16_t*>(feat + off));
-        h[i] = do_hid ? __ldg(reinterpret_cast<const uint16_t*>(hid + off)) : (uint16_t)0;
-      }
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t r = rg + 8 * i;
+      const size_t off = (size_t)r * 128 + ((u_in_blk ^ (r & 7)) << 4);
+      f[i] = __ldg(reinterpret_cast<const uint4*>(feat + off));
+      h[i] = do_hid ? __ldg(reinterpret_cast<const uint4*>(hid + off)) : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + i;
-        acc_wd = fmaf(s_dd[r], half_bits_to_float<kFmt>(f[i]), acc_wd);
-        const float hv = half_bits_to_float<kFmt>(h[i]);
+    for (int i = 0; i < 16; ++i) {
+      const int r = rg + 8 * i;
+      const float dd = s_dd[r];
+      const float d0 = s_ds[r][0], d1 = s_ds[r][1], d2 = s_ds[r][2];
+      const uint32_t fw[4] = {f[i].x, f[i].y, f[i].z, f[i].w}, hw[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc_w2[c] = fmaf(s_ds[r][c], hv, acc_w2[c]);
+      for (int k = 0; k < 4; ++k) {
+        const float2 fv = Half2Pack<kFmt>::unpack(fw[k]), hv = Half2Pack<kFmt>::unpack(hw[k]);
+        acc_wd[2 * k] = fmaf(dd, fv.x, acc_wd[2 * k]);
+        acc_wd[2 * k + 1] = fmaf(dd, fv.y, acc_wd[2 * k + 1]);
+        acc_w2[0][2 * k] = fmaf(d0, hv.x, acc_w2[0][2 * k]); acc_w2[0][2 * k + 1] = fmaf(d0, hv.y, acc_w2[0][2 * k + 1]);
+        acc_w2[1][2 * k] = fmaf(d1, hv.x, acc_w2[1][2 * k]); acc_w2[1][2 * k + 1] = fmaf(d1, hv.y, acc_w2[1][2 * k + 1]);
+        acc_w2[2][2 * k] = fmaf(d2, hv.x, acc_w2[2][2 * k]); acc_w2[2][2 * k + 1] = fmaf(d2, hv.y, acc_w2[2][2 * k + 1]);
       }
     }
-    if (j == 0)
+    if (t == 0)
       for (int r = 0; r < kTileM; ++r) acc_bd += s_dd[r];
-    if (j >= 1 && j <= C)
-      for (int r = 0; r < kTileM; ++r) acc_b2 += s_ds[r][j - 1];
+    if (t >= 1 && t <= C)
+      for (int r = 0; r < kTileM; ++r) acc_b2 += s_ds[r][t - 1];
   }
-  if (j < A.hidden_last) atomicAdd(p.grads + A.density_w_offset() + j, acc_wd);
-  if (j == 0) atomicAdd(p.grads + A.density_b_offset(), acc_bd);
-  if (j < A.hidden_dir)
-    for (int c = 0; c < C; ++c) atomicAdd(p.grads + A.color2_w_offset() + (int64_t)c * A.hidden_dir + j, acc_w2[c]);
-  if (j >= 1 && j <= C) atomicAdd(p.grads + A.color2_b_offset() + j - 1, acc_b2);
+  // fold the 8 row groups
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_red[rg][u * 8 + i] = acc_wd[i];
+    if (do_hid)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s_red[rg][kInner + c * kDirPad + u * 8 + i] = acc_w2[c][i];
+  }
+  __syncthreads();
+  for (int j = t; j < kInner + 3 * kDirPad; j += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += s_red[g][j];
+    if (j < kInner) {
+      if (j < A.hidden_last) atomicAdd(p.grads + A.density_w_offset() + j, v);
+    } else {
+      const int c = (j - kInner) / kDirPad, jj = (j - kInner) % kDirPad;
+      if (c < C && jj < A.hidden_dir) atomicAdd(p.grads + A.color2_w_offset() + (int64_t)c * A.hidden_dir + jj, v);
+    }
+  }
+  if (t == 0) atomicAdd(p.grads + A.density_b_offset(), acc_bd);
+  if (t >= 1 && t <= C) atomicAdd(p.grads + A.color2_b_offset() + t - 1, acc_b2);
 }
 
 // per-ray direction part of the colour hidden layer: dW_c[:, H + k] += sum_rays (sum_samples dY[ray, s, :]) emb27[ray][k]
