@@ -8,7 +8,8 @@ import torch
 from oracle import nerf_oracle as O
 from yanerf import synthetic as syn
 from yanerf.pipelines.utils import EvaluationMode, sample_grid, scatter_rays_to_image
-from yanerf.testing import build_pipeline, load_synth_nets, oracle_spec, pipeline_cfg
+from conftest import oracle_spec
+from yanerf.testing import build_pipeline, load_synth_nets, pipeline_cfg
 from yanerf.utils.config import ConfigDict
 
 pytestmark = pytest.mark.gpu

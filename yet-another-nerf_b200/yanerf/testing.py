@@ -1,5 +1,5 @@
 """Helpers shared by tests, bench.py and smoke(): build a lego.yml-shaped pipeline at a small image size,
-load seeded synthetic weights, and the matching oracle spec.  (No oracle import here: product package.)"""
+load seeded synthetic weights.  (Nothing here touches oracle/: this is the product package.)"""
 from __future__ import annotations
 
 from typing import Dict, List, Sequence
@@ -53,10 +53,3 @@ def load_synth_nets(pipe, seeds: Sequence[int], gain: float) -> List[Dict[str, t
         fn._fn.load_state_dict(sd)
         nets.append(sd)
     return nets
-
-
-def oracle_spec(H, W, n_fine, noise_std, chunk, min_depth=2.0, max_depth=6.0):
-    from oracle import nerf_oracle as O  # tests / smoke / bench only
-
-    return O.PipelineSpec(image_height=H, image_width=W, n_pts_fine=n_fine, density_noise_std_train=noise_std,
-                          chunk_size_grid=chunk, min_depth=min_depth, max_depth=max_depth)
