@@ -1,0 +1,18 @@
+"""Smallest end-to-end case for compute-sanitizer: one tiny train step + one tiny eval render."""
+import os, sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "yet-another-nerf_b200"))
+import torch
+from yanerf import synthetic as syn
+from yanerf.pipelines.utils import EvaluationMode
+from yanerf.testing import build_pipeline, load_synth_nets
+dev = "cuda"
+pipe = build_pipeline(8, 8, 24, 64, 0.2, 64 * 9).to(dev)
+load_synth_nets(pipe, (1, 2), 1.0)
+poses, focal, img = syn.synth_camera(1, 0).to(dev), torch.full((1, 1), 10.0, device=dev), syn.synth_image(1, 8, 8, 3).to(dev)
+out = pipe(poses=poses, focal_lengths=focal, image_rgb=img, evaluation_mode=EvaluationMode.TRAINING)
+out["objective"].mean().backward()
+with torch.no_grad():
+    ev = pipe(poses=poses, focal_lengths=focal, image_rgb=img, evaluation_mode=EvaluationMode.EVALUATION)
+torch.cuda.synchronize()
+print("ok", float(out["objective"].mean()), float(ev["objective"].mean()))
