@@ -133,7 +133,7 @@ def cpu_render_baseline(budget_s: float = 12.0):
         t0 = time.perf_counter()
         O.render_image(nets, spec, poses, focal, ray_slice=(start, start + per * n_chunks))
         dt = time.perf_counter() - t0
-    return dict(value=per * n_chunks / dt, unit="rays/s", cores=threads, kind="port",
+    return dict(value=per * n_chunks / dt, unit="rays/s", cores=threads, kind="port", sample_ms=dt * 1e3,
                 sample=f"{n_chunks} x {per}-ray chunks of the 800x800 lego render ({per * n_chunks} rays, {dt:.1f} s), "
                        f"torch {torch.__version__} CPU fp32")
 
@@ -143,16 +143,18 @@ def run_reference_arm(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    vals = []
+    vals, times = [], []
     base = None
     for i in range(args.warmup + steps):
         base = cpu_render_baseline(budget_s=max(2.0, 60.0 / (args.warmup + steps)))
         if i >= args.warmup:
             vals.append(base["value"])
+            times.append(base["sample_ms"])
     value = sum(vals) / len(vals)
     base["value"] = value
     line = dict(metric="render rays/sec (lego.yml 800x800, 64+128 samples)", value=value, unit="rays/s",
-                n_gpus=args.gpus, steps=steps, warmup=args.warmup, ms_per_step=None, higher_is_better=True,
+                n_gpus=args.gpus, steps=steps, warmup=args.warmup, ms_per_step=round(sum(times) / len(times), 1),
+                higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                 config={"workload": "lego.yml full 800x800 synthetic-camera render (inference, chunked, 64+128 samples)",
                         "note": "reference algorithm on host cores (oracle port), bounded ray sample per step"},
