@@ -50,6 +50,13 @@ int yn_ray_bundle(const float* poses, int64_t pose_batch_stride, int64_t pose_ro
                   float* lengths, float* xy_out, int64_t B, int64_t n, int P, int width, int height, int full_grid,
                   void* stream);
 
+/* Training pixel pick (ray_sampler.py:187-229, unmasked case: torch.multinomial(ones(H*W), n, replacement=False)):
+ * n distinct pixels per image, uniformly at random, by a keyed Feistel permutation with cycle walking.
+ *   seed  int64[1] in DEVICE memory (so a captured CUDA graph can be replayed with a bumped seed)
+ *   out: idx int64 [B,n] flat pixel indices (x + W*y), xy float [B,n,2] or NULL */
+int yn_sample_pixels(const int64_t* seed, int64_t* idx, float* xy, int64_t B, int64_t n, int width, int height,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * NeRF MLP (yanerf/pipelines/models/nerf_mlp.py:12-289, models/utils.py:17-245).
  * Architecture family: inner trunk width 256 (the reference never forwards hidden_dim, nerf_mlp.py:88-95),
@@ -151,6 +158,11 @@ int yn_sample_pdf(const float* bins, const float* weights, const float* u, int64
  * ---------------------------------------------------------------------------------------------- */
 int yn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                  float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+
+/* Same update with the step counter and learning rate read from DEVICE memory (state[0] = step as float >= 1,
+ * state[1] = lr): the launch can be part of a captured CUDA graph. */
+int yn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const float* state, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -420,3 +420,29 @@ def ctypes_ptr(t):
     import ctypes
 
     return ctypes.c_void_p(t.data_ptr())
+
+
+def test_pixel_sampler_distinct_uniform():
+    """yn_sample_pixels: n distinct in-range pixels per image, different per image and per seed, uniform marginals."""
+    from yanerf import ops
+
+    H, W, B, n = 37, 53, 3, 700
+    seed = torch.tensor([12345], dtype=torch.int64, device=DEV)
+    idx, xy = ops.sample_pixels(seed, B, n, W, H)
+    assert idx.shape == (B, n) and int(idx.min()) >= 0 and int(idx.max()) < H * W
+    for b in range(B):
+        assert idx[b].unique().numel() == n
+    assert not torch.equal(idx[0], idx[1])
+    assert torch.equal(xy[..., 0].long() + W * xy[..., 1].long(), idx)
+    idx2, _ = ops.sample_pixels(seed + 1, B, n, W, H)
+    assert not torch.equal(idx, idx2)
+    full, _ = ops.sample_pixels(seed, 1, H * W, W, H)  # n == H*W: a permutation
+    assert torch.equal(full[0].sort()[0], torch.arange(H * W, device=DEV))
+    # uniformity: 2000 draws of 64 pixels from a 16x16 image, chi-square over the 256 cells
+    counts = torch.zeros(256, device=DEV)
+    for s in range(200):
+        d, _ = ops.sample_pixels(seed + 100 + s, 10, 64, 16, 16)
+        counts += torch.bincount(d.reshape(-1), minlength=256).float()
+    expected = 200 * 10 * 64 / 256
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    assert chi2 < 255 + 6 * (2 * 255) ** 0.5, chi2  # mean 255, sigma ~22.6

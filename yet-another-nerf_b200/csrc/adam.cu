@@ -40,3 +40,39 @@ extern "C" int yn_adam_step(float* params, const float* grads, float* exp_avg, f
       params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
   return ynb::check_launch("yn_adam_step");
 }
+
+// Graph-friendly variant: the step counter and the learning rate live in device memory (state[0] = step as float,
+// bumped by the caller on the stream; state[1] = lr), so a captured CUDA graph replays with fresh values.
+namespace ynb {
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       const float* __restrict__ state, float b1, float b2, float eps,
+                                                       float gscale) {
+  const float step = state[0], lr = state[1];
+  const float bc1 = 1.f - powf(b1, step);
+  const float sqrt_bc2 = sqrtf(1.f - powf(b2, step));
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrt_bc2 + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+  }
+}
+}  // namespace ynb
+
+extern "C" int yn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const float* state, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (n < 0) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_adam_step_dev: n < 0");
+  if (n == 0) return YN_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state)
+    return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_adam_step_dev: null pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ynb::adam_dev_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n,
+                                                                                      state, beta1, beta2, eps, grad_scale);
+  return ynb::check_launch("yn_adam_step_dev");
+}

@@ -3,6 +3,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <mutex>
+#include <set>
+
 #include "mlp_common.cuh"
 
 namespace ynb {
@@ -21,6 +24,13 @@ int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(YN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return YN_OK;
+}
+
+bool first_use(const void* kernel) {
+  static std::mutex mu;
+  static std::set<const void*> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(kernel).second;
 }
 
 int check_arch(const yn_mlp_arch* a) {

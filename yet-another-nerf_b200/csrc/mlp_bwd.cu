@@ -683,8 +683,10 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
   if (n_splits < 1) n_splits = 1;
   if (n_splits > n_tiles) n_splits = (int)n_tiles;
   auto run = [&](auto dgrad, auto wgrad, auto heads, auto dir) {
-    cudaFuncSetAttribute(dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
-    cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+    if (first_use(reinterpret_cast<const void*>(dgrad)))
+      cudaFuncSetAttribute(dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+    if (first_use(reinterpret_cast<const void*>(wgrad)))
+      cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
     dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
     wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
     heads<<<(int)(n_tiles < 4 * sms ? n_tiles : 4 * sms), 256, 0, stream>>>(p);

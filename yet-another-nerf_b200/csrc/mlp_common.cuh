@@ -121,5 +121,6 @@ inline Arch arch_from_c(const yn_mlp_arch* a) {
 int fail(int code, const char* fmt, ...);
 int check_arch(const yn_mlp_arch* a);
 int check_launch(const char* what);
+bool first_use(const void* kernel);  // true the first time a kernel pointer is seen (one-time attribute setup)
 
 }  // namespace ynb

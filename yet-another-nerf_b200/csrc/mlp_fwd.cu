@@ -431,7 +431,10 @@ static int launch_fwd(const FwdParams& p, cudaStream_t stream) {
   const int grid = (int)(n_pairs < sms ? n_pairs : sms);
   if (grid == 0) return YN_OK;
   auto run = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
+    // once per kernel (all instantiations share one pointer type, so key on the pointer); not a stream operation,
+    // and kept out of stream capture this way
+    if (first_use(reinterpret_cast<const void*>(kern)))
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes);
     kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(p);
   };
   const bool st = p.stash != nullptr;

@@ -85,3 +85,61 @@ extern "C" int yn_ray_bundle(const float* poses, int64_t pose_batch_stride, int6
   ynb::ray_bundle_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return ynb::check_launch("yn_ray_bundle");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Pixel pick for training: n DISTINCT pixels per image, uniformly at random (what
+// `torch.multinomial(ones(H*W), n, replacement=False)` draws in _RaySampler.forward, ray_sampler.py:187-229, for the
+// unmasked case).  A keyed Feistel permutation of [0, 2^k) with cycle walking maps i = 0..n-1 to distinct pixels in
+// O(n) -- no pass over the H*W weights.  The 64-bit seed is read from device memory so that a captured CUDA graph
+// draws new pixels on every replay (the runner bumps it on the stream).
+// ------------------------------------------------------------------------------------------------
+namespace ynb {
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) sample_pixels_kernel(const int64_t* __restrict__ seed_ptr, int64_t* __restrict__ idx,
+                                                           float* __restrict__ xy, int64_t B, int64_t n, int64_t n_pix,
+                                                           int width, int half_bits) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * n) return;
+  const int64_t b = t / n;
+  const uint64_t seed = (uint64_t)seed_ptr[0] + 0x9E3779B97F4A7C15ULL * (uint64_t)(b + 1);
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint64_t v = (uint64_t)(t % n);
+  do {  // cycle-walk until the permuted value is a valid pixel (expected < 4 rounds: 2^(2*half_bits) < 4 * n_pix)
+    uint32_t l = (uint32_t)(v >> half_bits) & mask, r = (uint32_t)v & mask;
+#pragma unroll
+    for (int round = 0; round < 6; ++round) {
+      const uint32_t key = (uint32_t)(seed >> (8 * (round & 3))) + 0x85ebca6bU * (round + 1);
+      const uint32_t f = mix32(r ^ key) & mask;
+      const uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    v = ((uint64_t)l << half_bits) | r;
+  } while (v >= (uint64_t)n_pix);
+  idx[t] = (int64_t)v;
+  if (xy) {
+    xy[2 * t] = (float)(v % width);
+    xy[2 * t + 1] = (float)(v / width);
+  }
+}
+
+}  // namespace ynb
+
+extern "C" int yn_sample_pixels(const int64_t* seed, int64_t* idx, float* xy, int64_t B, int64_t n, int width, int height,
+                                void* stream) {
+  const int64_t n_pix = (int64_t)width * height;
+  if (B < 0 || n < 0 || width < 1 || height < 1 || n > n_pix)
+    return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_sample_pixels: need 0 <= n <= width*height");
+  if (B * n == 0) return YN_OK;
+  if (!seed || !idx) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_sample_pixels: null pointer");
+  int half_bits = 1;
+  while (((int64_t)1 << (2 * half_bits)) < n_pix) ++half_bits;
+  ynb::sample_pixels_kernel<<<(unsigned)((B * n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      seed, idx, xy, B, n, n_pix, width, half_bits);
+  return ynb::check_launch("yn_sample_pixels");
+}

@@ -343,7 +343,11 @@ static void launch_fast(const ynb::PdfParams& p, cudaStream_t st) {
   const int wpb = 8;
   const size_t smem = (size_t)wpb * (CDFN + 2 * P + p.sort_pow2) * sizeof(float);
   auto kern = ynb::sample_pdf_merge_fast_kernel<PS, NPL>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured = 0;  // per instantiation; the size only depends on (PS, NPL)
+  if (configured < smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
   kern<<<(unsigned)((p.R + wpb - 1) / wpb), wpb * 32, smem, st>>>(p);
 }
 
@@ -385,7 +389,11 @@ static int launch_pdf(const float* lengths, const float* weights, const float* u
   const int wpb = 8;
   const size_t smem = (size_t)wpb * (3 * P + n2) * sizeof(float);
   if (smem > 200 * 1024) return ynb::fail(YN_ERR_UNSUPPORTED, "yn_sample_pdf_merge: P + n_new too large for shared memory");
-  cudaFuncSetAttribute(ynb::sample_pdf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t configured = 0;
+  if (configured < smem) {
+    cudaFuncSetAttribute(ynb::sample_pdf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
   ynb::sample_pdf_merge_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, smem, st>>>(p);
   return ynb::check_launch("yn_sample_pdf_merge");
 }

@@ -55,6 +55,7 @@ SYMBOLS = {
     "yn_version": (c_int, []),
     "yn_last_error_string": (c_char_p, []),
     "yn_ray_bundle": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "yn_sample_pixels": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),
     "yn_mlp_param_count": (c_int64, [POINTER(MlpArch)]),
     "yn_mlp_wpack_bytes": (c_int64, [POINTER(MlpArch)]),
     "yn_mlp_aux_floats": (c_int64, [POINTER(MlpArch)]),
@@ -69,6 +70,7 @@ SYMBOLS = {
     "yn_sample_pdf_merge": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "yn_sample_pdf": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "yn_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, c_float, _P]),
+    "yn_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

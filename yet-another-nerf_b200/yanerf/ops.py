@@ -93,6 +93,16 @@ def ray_bundle(
     return origins, directions, lengths, xys
 
 
+def sample_pixels(seed: torch.Tensor, batch: int, n: int, width: int, height: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """n distinct uniformly random pixels per image (the unmasked `torch.multinomial` pick of the reference's
+    ray sampler).  seed: int64[1] CUDA tensor.  Returns idx int64 [B,n] and xy float [B,n,2]."""
+    idx = torch.empty(batch, n, dtype=torch.int64, device=seed.device)
+    xy = torch.empty(batch, n, 2, device=seed.device)
+    _call("yn_sample_pixels", N.ptr(seed, torch.int64), N.ptr(idx, torch.int64), N.ptr(xy), batch, n, width, height,
+          N.stream_ptr())
+    return idx, xy
+
+
 # --------------------------------------------------------------------------- #
 # NeRF MLP
 # --------------------------------------------------------------------------- #
@@ -346,3 +356,9 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.9
             N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
             int(step), grad_scale, N.stream_ptr(),
         )
+
+
+def adam_step_dev(params, grads, exp_avg, exp_avg_sq, state, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """Adam with step / lr read from the device tensor `state` = [step, lr] (CUDA-graph friendly)."""
+    _call("yn_adam_step_dev", N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(),
+          N.ptr(state), beta1, beta2, eps, grad_scale, N.stream_ptr())

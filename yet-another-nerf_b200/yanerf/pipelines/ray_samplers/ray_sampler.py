@@ -65,6 +65,11 @@ class _RaySampler(torch.nn.Module):
         self._n_rays_per_image = n_rays_per_image
         self._unit_directions = unit_directions  # stored, never applied (reference behaviour)
         self._stratified_sampling = stratified_sampling
+        # Unmasked training pick through `yn_sample_pixels` instead of torch.multinomial over H*W weights (same
+        # distribution: a uniformly random n-subset; O(n) and CUDA-graph friendly).  Off by default: the reference
+        # consumes torch's global generator here.  FusedTrainer turns it on.
+        self.fused_pixel_sampler = False
+        self._pixel_seed: Optional[torch.Tensor] = None
 
     def forward(self, poses, focal_lengths, *, image_height=None, image_width=None, mask=None,
                 sampling_prob_mask=None, min_depth=None, max_depth=None,
@@ -84,10 +89,11 @@ class _RaySampler(torch.nn.Module):
         spatial: Tuple[int, ...] = (H, W)
         if num_rays is not None:
             plain = mask is None and sampling_prob_mask is None
+            fused = plain and self.fused_pixel_sampler and isinstance(num_rays, int) and poses.is_cuda
             if mask is not None:
                 assert tuple(mask.shape) == (B, H, W)
                 weights = mask.reshape(B, -1).float()
-            else:
+            elif not fused:
                 weights = torch.ones(B, H * W, device=device)
             if sampling_prob_mask is not None:
                 if tuple(sampling_prob_mask.shape) == (B, H, W):
@@ -110,11 +116,18 @@ class _RaySampler(torch.nn.Module):
                     raise ValueError(
                         f"Invalida `sampling_prob_mask`, shape of {sampling_prob_mask.shape}, want (B, H, W) or (B, L, H, W)"
                     )
-            if weights.ndim == 2:
+            xy_fused = None
+            if fused:
+                if self._pixel_seed is None or self._pixel_seed.device != device:
+                    # seeded from torch's CPU generator: reproducible under torch.manual_seed, no device sync
+                    self._pixel_seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(device)
+                rays_idx, xy_fused = ops.sample_pixels(self._pixel_seed, B, num_rays, W, H)
+                self._pixel_seed += 1
+            elif weights.ndim == 2:
                 rays_idx = _safe_multinomial(weights, num_rays, all_positive=plain)
             else:
                 rays_idx = torch.cat([_safe_multinomial(weights[:, i], num_rays[i]) for i in range(len(num_rays))], dim=-1)
-            xy = torch.stack((rays_idx % W, rays_idx // W), dim=-1).float()
+            xy = xy_fused if xy_fused is not None else torch.stack((rays_idx % W, rays_idx // W), dim=-1).float()
             spatial = (rays_idx.shape[1], 1)
 
         min_depth = self._min_depth if min_depth is None else min_depth

@@ -17,7 +17,8 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
     n_rays = 4096
     peaks = B.load_peaks()
     pipe, _ = B.build_lego_pipeline(dev, n_rays=n_rays)
-    trainer = FusedTrainer(pipe, lr=5e-4 * world)  # linear LR scaling, scripts/run.py:152-156
+    use_graph = os.environ.get("YANERF_TRAIN_GRAPH", "1") != "0"
+    trainer = FusedTrainer(pipe, lr=5e-4 * world, use_cuda_graph=use_graph)  # linear LR scaling, scripts/run.py:152-156
     poses, focal, image = B.synthetic_inputs(rank)
     batch_d = dict(poses=poses.to(dev), focal_lengths=focal.to(dev), image_rgb=image.to(dev))
     host = dict(poses=poses.pin_memory(), focal_lengths=focal.pin_memory(), image_rgb=image.pin_memory())
@@ -28,7 +29,7 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
         return trainer.train_step(batch_d)
 
     def step_e2e():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        b = host if use_graph else {k: v.to(dev, non_blocking=True) for k, v in host.items()}  # graph: H2D into static inputs
         preds = trainer.train_step(b)
         loss_h.copy_(preds["objective"], non_blocking=True)
         return preds
@@ -51,23 +52,26 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(5, args.warmup)):  # includes the 3 eager steps before the graph is captured
         step_resident()
     torch.cuda.synchronize()
     sampler = B.ClockSampler(dev.index or 0)
     if rank == 0:
         sampler.start()
-    ops.Profiler.reset()
-    ops.Profiler.enabled = True
-    l0 = ops.Profiler.launches
     total_ms = timed(step_resident, args.steps)
-    ops.Profiler.enabled = False
-    launches = (ops.Profiler.launches - l0) // max(1, args.steps)
-    prof = ops.Profiler.summary()
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
+    # per-kernel times and the launch count come from the same step run eagerly (a graph replay makes the same launches
+    # but bypasses the host-side event brackets)
+    ops.Profiler.reset()
+    ops.Profiler.enabled = True
+    l0 = ops.Profiler.launches
+    timed(lambda: trainer.eager_step(batch_d), args.steps)
+    ops.Profiler.enabled = False
+    launches = (ops.Profiler.launches - l0) // max(1, args.steps)
+    prof = ops.Profiler.summary()
     trainer.finish()
 
     rays = n_rays * world
@@ -83,6 +87,7 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16 operands, f32 accumulate / master weights",
             data="synthetic",
             config={"workload": "lego.yml training step, 4096 rays/GPU, coarse+fine fwd/bwd + Adam, ray-sharded DDP",
+                    "cuda_graph": use_graph,
                     "l2": "stash + gradient stash of one step (~10 GB) exceed the 126 MB L2", "parallelism": f"dp{world}"},
             clocks=clocks, gpu_launches=int(launches),
             e2e={"value": round(e2e_value, 1), "unit": "rays/s", "ms_per_step": round(e2e_ms / args.steps, 3),

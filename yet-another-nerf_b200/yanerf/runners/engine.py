@@ -31,8 +31,18 @@ class FusedTrainer:
     """Owns flat parameter / gradient / Adam-moment buffers of a pipeline and performs one optimisation step."""
 
     def __init__(self, pipeline: torch.nn.Module, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group: Optional[Any] = None) -> None:
+                 process_group: Optional[Any] = None, use_cuda_graph: bool = False, graph_warmup_steps: int = 3) -> None:
+        """use_cuda_graph: after `graph_warmup_steps` eager steps the whole iteration (pixel pick, forward, backward,
+        all-reduce, Adam, weight re-pack) is captured once and replayed; step counter, learning rate and the pixel
+        seed live in device memory so every replay sees fresh values."""
         self.pipeline = pipeline
+        self.use_cuda_graph = use_cuda_graph
+        self._graph_warmup = graph_warmup_steps
+        self._graph = None
+        self._side_stream = None
+        self._warm_steps = 0
+        self._static_batch: Dict[str, Any] = {}
+        self._static_preds: Dict[str, Any] = {}
         self.lr, self.betas, self.eps = lr, betas, eps
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -54,6 +64,11 @@ class FusedTrainer:
                 p.grad = self.flat_grad[off:off + k].view_as(p)
                 off += k
         self.step_count = 0
+        self._state = torch.zeros(2, device=dev)  # [step, lr] read by yn_adam_step_dev
+        self._lr_host = torch.zeros(1).pin_memory() if dev.type == "cuda" else torch.zeros(1)
+        for m in pipeline.modules():  # O(n) graph-friendly pixel pick instead of torch.multinomial over H*W
+            if hasattr(m, "fused_pixel_sampler"):
+                m.fused_pixel_sampler = True
         self._flag_host, self._flag_event, self._flag_pending = None, None, False
         # no device->host sync inside the step: pixel-grid range checks move to the host (shapes) and the refiner's
         # "Negative weights provided." flag is read once, after the whole step has been queued
@@ -90,16 +105,71 @@ class FusedTrainer:
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
 
-    def train_step(self, batch: Dict[str, Any], lr: Optional[float] = None) -> Dict[str, torch.Tensor]:
-        """forward (TRAINING) -> objective.mean().backward() -> all-reduce -> Adam.  Returns the preds dict."""
+    def eager_step(self, batch: Dict[str, Any], lr: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """One step outside the CUDA graph (same kernels, launched one by one)."""
+        preds = self._eager_step(batch, lr)
+        self._deferred_checks()
+        return preds
+
+    def _eager_step(self, batch: Dict[str, Any], lr: Optional[float]) -> Dict[str, torch.Tensor]:
         self.zero_grad()
         preds = self.pipeline(**batch, evaluation_mode=EvaluationMode.TRAINING)
         if "objective" not in preds:
             raise KeyError("objective")  # runners/apis.py:90-91
         preds["objective"].mean().backward()
         self.optimizer_step(lr)
-        self._deferred_checks()
         return preds
+
+    def train_step(self, batch: Dict[str, Any], lr: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """forward (TRAINING) -> objective.mean().backward() -> all-reduce -> Adam.  Returns the preds dict (with
+        `use_cuda_graph` the same static tensors every step: read them before the next call)."""
+        if not self.use_cuda_graph or self.flat.device.type != "cuda":
+            preds = self._eager_step(batch, lr)
+            self._deferred_checks()
+            return preds
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        if self._graph is None and self._warm_steps < self._graph_warmup:
+            # warm-up on the capture stream (autograd remembers the stream a node was first run on): fills the
+            # linspace / allocator caches and configures the kernels
+            self._warm_steps += 1
+            self._side_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side_stream):
+                preds = self._eager_step(batch, lr)
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._deferred_checks()
+            return preds
+        self._lr_host[0] = self.lr if lr is None else lr
+        if self._graph is None:
+            self._capture(batch)
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self._static_batch[k].copy_(v, non_blocking=True)
+        self._state[1:2].copy_(self._lr_host, non_blocking=True)
+        self._graph.replay()  # (the captured forward starts by re-packing the weight images from the flat buffer)
+        self.step_count += 1
+        self._invalidate()    # other weight images (e.g. the fp16 one used by evaluation) are stale now
+        self._deferred_checks()
+        return self._static_preds
+
+    def _capture(self, batch: Dict[str, Any]) -> None:
+        self._static_batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        self._state[0] = float(self.step_count)
+        self._state[1:2].copy_(self._lr_host, non_blocking=True)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=self._side_stream):
+            self.flat_grad.zero_()
+            preds = self.pipeline(**self._static_batch, evaluation_mode=EvaluationMode.TRAINING)
+            if "objective" not in preds:
+                raise KeyError("objective")
+            preds["objective"].mean().backward()
+            if self.world > 1:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self._state[0:1] += 1.0
+            ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._state, self.betas[0],
+                              self.betas[1], self.eps, grad_scale=1.0 / self.world)
+            self._static_preds = {k: v.detach() if torch.is_tensor(v) else v for k, v in preds.items()}
 
     def _deferred_checks(self) -> None:
         """The refiner's device flag of step k is copied to pinned memory asynchronously and examined at the end of
@@ -135,6 +205,8 @@ class FusedTrainer:
         self.step_count += 1
         ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr if lr is None else lr,
                       self.step_count, self.betas[0], self.betas[1], self.eps, grad_scale=1.0 / self.world)
+        if self._graph is not None:
+            self._state[0:1].fill_(float(self.step_count))  # keep the graph's device-side step counter in sync
         self._invalidate()
 
     # checkpoint format of scripts/run.py:416-422 (model state_dict + optimizer state + epoch)
@@ -149,4 +221,5 @@ class FusedTrainer:
             self.exp_avg.copy_(opt["exp_avg"])
             self.exp_avg_sq.copy_(opt["exp_avg_sq"])
             self.step_count = int(opt["step"])
+            self._state[0:1].fill_(float(self.step_count))
         self._invalidate()
