@@ -18,6 +18,7 @@
 // the epilogue of half 0 (-> activation blocks 0,1 of the next layer) runs while half 1 is still being multiplied,
 // and the next layer starts on blocks 0,1 while the epilogue of half 1 fills blocks 2,3.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "mlp_common.cuh"
@@ -47,11 +48,52 @@ struct FwdParams {
   uint8_t* stash;  // nullptr in inference
   int64_t n_points;
   int P;
+  long long* trace;  // timing experiments only (YN_FWD_TRACE=<file>): CTA 0 logs (tag, clock64) pairs, 4 roles x 2048 events
   int debug;  // timing experiments only (YN_FWD_DEBUG bit mask): 1 = epilogue skips TMEM/STS work, 2 = producer skips the copies
+};
+
+constexpr int kTraceEvents = 2048;
+struct Tracer {
+  long long* buf;
+  int n;
+  __device__ __forceinline__ void init(long long* base, int role) {
+    buf = (base && blockIdx.x == 0) ? base + (size_t)role * 2 * kTraceEvents : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void log(int tag) {
+    if (buf && n < kTraceEvents) {
+      buf[2 * n] = tag;
+      buf[2 * n + 1] = clock64();
+      ++n;
+    }
+  }
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// sin / cos of x * 2^k for the harmonic embedding.  The reference evaluates sin(fl32(x * 2^k)) and x * 2^k is exact, so
+// the phase is reduced once per coordinate: x / (2 pi) as an unevaluated fp32 pair (hi + lo, ~48 bits; this GPU's fp64
+// rate is too low for the job), scaled by 2^k exactly, fractional part of `hi` exact, `lo` added back.  Remaining error:
+// one fp32 rounding of the reduced angle in [-pi, pi] (1.9e-7) + the SFU approximation (4e-7 abs on that range):
+// < 1e-6 absolute at every octave, 1/250 of the fp16 operand ulp.  ~8 instructions instead of sincosf's ~50.
+constexpr float kInvTwoPiHi = 0.15915494309189535f;
+constexpr float kInvTwoPiLo = static_cast<float>(0.15915494309189533577 - static_cast<double>(kInvTwoPiHi));
+struct Turns {
+  float hi, lo;
+};
+__device__ __forceinline__ Turns to_turns(float x) {
+  Turns t;
+  t.hi = __fmul_rn(x, kInvTwoPiHi);
+  t.lo = __fmaf_rn(x, kInvTwoPiLo, __fmaf_rn(x, kInvTwoPiHi, -t.hi));
+  return t;
+}
+__device__ __forceinline__ void harmonic_sincos(const Turns& t, int k, float& sn, float& cs) {
+  const float scale = static_cast<float>(1 << k);
+  const float v = t.hi * scale;
+  const float r = (v - rintf(v)) + t.lo * scale;  // [-0.5, 0.5] turns
+  __sincosf(r * 6.283185307179586f, &sn, &cs);
 }
 
 template <int kFmt>
@@ -107,7 +149,7 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_addr, int c_lo, const f
         }
         if (kMode == 2) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 3; ++c) {  // color_dim <= 3
             const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0 + j));
             acc[c] = fmaf(x0, w.x, acc[c]); acc[c] = fmaf(x1, w.y, acc[c]);
             acc[c] = fmaf(x2, w.z, acc[c]); acc[c] = fmaf(x3, w.w, acc[c]);
@@ -214,6 +256,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       const uint32_t act_base = s_act + g * 4 * kBlkBytes, emb_base = s_emb + g * kBlkBytes;
       uint32_t slot = 0, phase = 0;
       uint32_t ed_phase0 = 0, ed_phase1 = 0;
+      Tracer tr;
+      tr.init(p.trace, g);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           const int nkbh = A.nkb_hidden(l);
@@ -221,21 +265,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           const int nnh = A.nnh(l);
           const int kb_free = nkb > 1 ? 1 : 0;
           const bool has_bias = A.has_bias_stage(l);
+          tr.log(l << 8 | 0);
           mbar_wait(my_epi, ed_phase0);
           ed_phase0 ^= 1;
           tc_fence_after();
+          tr.log(l << 8 | 1);
           bool waited1 = false;
           for (int nh = 0; nh < nnh; ++nh) {
             const uint32_t d_tmem = tmem_base + g * 256 + nh * 128;
             for (int kb = 0; kb < nkb; ++kb) {
               if (!waited1 && (nh == 1 || (kb >= 2 && kb < nkbh))) {
+                tr.log(l << 8 | 2);
                 mbar_wait(my_epi + 8, ed_phase1);
                 ed_phase1 ^= 1;
                 tc_fence_after();
                 waited1 = true;
+                tr.log(l << 8 | 3);
               }
               mbar_wait(bar_full + 8 * slot, phase);
               tc_fence_after();
+              tr.log(l << 8 | 16 | (nh << 3) | kb);
               const uint64_t b_desc = umma_desc_kmajor(s_ring + slot * kBlkBytes);
               const uint64_t a_desc = umma_desc_kmajor((kb < nkbh) ? (act_base + kb * kBlkBytes) : emb_base);
 #pragma unroll
@@ -255,6 +304,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
               if (++slot == kRing) { slot = 0; phase ^= 1; }
             }
             umma_commit(my_hfull + 8 * nh);
+            tr.log(l << 8 | 4 | nh);
           }
           if (!waited1) {
             mbar_wait(my_epi + 8, ed_phase1);
@@ -279,13 +329,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     const int nfx = A.n_freq_xyz;
     const int blocks_per_tile = A.stash_blocks_per_tile();
     uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0;
+    Tracer tr;
+    tr.init(q == 0 && lane == 0 ? p.trace : nullptr, 2 + g);
     int l_emb_last = 0;  // last layer that reads the embedding block as an operand
     for (int l = 1; l < A.n_layers; ++l)
       if (A.has_emb(l)) l_emb_last = l;
 
     // harmonic embedding (models/utils.py:90-103) of row `row` of tile `t` -> this tile's embedding block:
-    // [sin(x f_k) | cos(x f_k) | x], channel a*L+k, channel 63 = 1 (bias).  (A double-angle recurrence from the base
-    // octave was tried: its error triples per octave, 8e-4 at 2^9, visible against the fp16 operand ulp -- rejected.)
+    // [sin(x f_k) | cos(x f_k) | x], channel a*L+k, channel 63 = 1 (bias).  x * 2^k is exact in fp32, so the phase
+    // is reduced once per coordinate (see harmonic_sincos); no error growth with the octave.
+    // (A double-angle recurrence from the base octave was tried: its error triples per octave, 8e-4 at 2^9 -- rejected.)
     auto write_embedding = [&](int64_t t) {
       const int64_t gi = t * kTileM + row;
       const bool ok = gi < p.n_points;
@@ -297,11 +350,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         for (int a = 0; a < 3; ++a)
           pt[a] = __fadd_rn(__ldg(p.origins + r * 3 + a), __fmul_rn(z, __ldg(p.directions + r * 3 + a)));
       }
+      if (nfx == 10) {
+        // lego / fern shape: whole 64-channel row assembled in registers, eight conflict-free 16-byte stores
+        uint32_t pk[32];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const Turns turns = to_turns(pt[a]);
+#pragma unroll
+          for (int k = 0; k < 10; k += 2) {
+            float s0, c0, s1, c1;
+            harmonic_sincos(turns, k, s0, c0);
+            harmonic_sincos(turns, k + 1, s1, c1);
+            if (!ok) { s0 = s1 = c0 = c1 = 0.f; }
+            pk[(a * 10 + k) >> 1] = Half2Pack<kFmt>::pack(s0, s1);
+            pk[(30 + a * 10 + k) >> 1] = Half2Pack<kFmt>::pack(c0, c1);
+          }
+        }
+        pk[30] = Half2Pack<kFmt>::pack(pt[0], pt[1]);
+        pk[31] = Half2Pack<kFmt>::pack(pt[2], 1.f);
+        const uint32_t row_base = emb_g + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(row_base + ((static_cast<uint32_t>(c) ^ swz) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        return;
+      }
       for (int a = 0; a < 3; ++a) {
-        float f = 1.f;
-        for (int k = 0; k < nfx; ++k, f *= 2.f) {
+        const Turns turns = to_turns(pt[a]);
+        for (int k = 0; k < nfx; ++k) {
           float sn, cs;
-          sincosf(pt[a] * f, &sn, &cs);  // full-accuracy range reduction: arguments reach 2^9 * 6 rad
+          harmonic_sincos(turns, k, sn, cs);
           if (!ok) { sn = 0.f; cs = 0.f; }
           const int ch = a * nfx + k;
           st_shared_u16(emb_g + sw128_offset(row, ch), to_half_bits<kFmt>(sn));
@@ -351,11 +428,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         const float* wd = p.aux + A.aux_wd();
         const float* w2 = p.aux + A.aux_w2();
         // ---- half 0: accumulator columns [0,128) -> activation blocks 0,1
+        tr.log(l << 8 | 0);
         mbar_wait(my_hfull, hf_phase0);
         hf_phase0 ^= 1;
+        tr.log(l << 8 | 1);
         mbar_wait(my_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
         b01_phase ^= 1;
         tc_fence_after();
+        tr.log(l << 8 | 2);
         if (kStash) {
           if (stash_leader) bulk_wait_read<0>();  // the previous layer's stash store has read the buffer
           named_bar_sync(1 + g, 128);
@@ -371,11 +451,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         fence_proxy_async_smem();
         // the last layer feeds no MMA: the next pair's embedding arrival (program order) covers the TMEM hand-over
         if (!is_color) mbar_arrive(my_epi);
+        tr.log(l << 8 | 3);
         // ---- half 1: columns [128,256) -> blocks 2,3 (the colour hidden layer is 128 wide: nothing to do)
         if (!is_color) {
           mbar_wait(my_hfull + 8, hf_phase1);
           hf_phase1 ^= 1;
           tc_fence_after();
+          tr.log(l << 8 | 4);
           if (p.debug & 1) {
           } else if (is_inter)
             epilogue_half<kFmt, 1, true>(t_row, 128, bias, wd, false, dens, w2, acc, act_row, swz);
@@ -385,6 +467,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           fence_proxy_async_smem();
         }
         if (!is_color) mbar_arrive(my_epi + 8);
+        tr.log(l << 8 | 5);
         if (l == l_emb_last && pair + gridDim.x < n_pairs) {
           // every MMA that reads this tile's embedding as an operand has completed (half_full[1] of this layer):
           // prefetch the next pair's embedding now, in the shadow of the remaining layers.  Later bias MMAs read
@@ -472,6 +555,25 @@ extern "C" int yn_mlp_fwd(const yn_mlp_arch* arch, const float* origins, const f
   {
     const char* dbg = getenv("YN_FWD_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+  }
+  p.trace = nullptr;
+  if (const char* path = getenv("YN_FWD_TRACE")) {  // debug aid: synchronous, one launch per file
+    const size_t n = (size_t)4 * 2 * ynb::kTraceEvents;
+    long long* dev = nullptr;
+    cudaMalloc(&dev, n * sizeof(long long));
+    cudaMemset(dev, 0, n * sizeof(long long));
+    p.trace = dev;
+    const int rc = ynb::launch_fwd(p, static_cast<cudaStream_t>(stream));
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    long long* host = (long long*)malloc(n * sizeof(long long));
+    cudaMemcpy(host, dev, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(path, "wb")) {
+      fwrite(host, sizeof(long long), n, f);
+      fclose(f);
+    }
+    free(host);
+    cudaFree(dev);
+    return rc;
   }
   return ynb::launch_fwd(p, static_cast<cudaStream_t>(stream));
 }
