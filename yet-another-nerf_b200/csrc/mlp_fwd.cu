@@ -176,6 +176,38 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_addr, int c_lo, const f
   }
 }
 
+// Plain 256-wide layers (no head attached): the whole 128-column half is pulled out of TMEM with one wait, converted
+// (ReLU fused into the conversion), and only then `before_store` runs -- for half 0 that is the wait until this layer's
+// MMAs have stopped reading activation blocks 0,1 -- so the TMEM latency and the conversions sit in the shadow of
+// the MMAs that are still running.
+template <int kFmt, bool kRelu, typename BeforeStore>
+__device__ __forceinline__ void epilogue_half_plain(uint32_t t_addr, int c_lo, uint32_t act_row, uint32_t swz,
+                                                    BeforeStore&& before_store) {
+  uint32_t v[4][32];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tmem_ld32(t_addr + c_lo + q * 32, v[q]);
+  tmem_ld_wait();
+  uint32_t pk[64];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float x0 = __uint_as_float(v[q][j]), x1 = __uint_as_float(v[q][j + 1]);
+      pk[q * 16 + j / 2] = kRelu ? pack_relu<kFmt>(x0, x1) : Half2Pack<kFmt>::pack(x0, x1);
+    }
+  before_store();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c0 = c_lo + q * 32;
+    const uint32_t blk = act_row + (c0 >> 6) * kBlkBytes;
+    const uint32_t u0 = ((c0 >> 5) & 1) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[q * 16 + 4 * i], pk[q * 16 + 4 * i + 1], pk[q * 16 + 4 * i + 2],
+                   pk[q * 16 + 4 * i + 3]);
+  }
+}
+
 template <int kFmt, bool kStash>
 __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -432,21 +464,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         mbar_wait(my_hfull, hf_phase0);
         hf_phase0 ^= 1;
         tr.log(l << 8 | 1);
-        mbar_wait(my_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
-        b01_phase ^= 1;
         tc_fence_after();
-        tr.log(l << 8 | 2);
-        if (kStash) {
-          if (stash_leader) bulk_wait_read<0>();  // the previous layer's stash store has read the buffer
-          named_bar_sync(1 + g, 128);
-        }
+        auto before_store0 = [&] {
+          mbar_wait(my_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
+          b01_phase ^= 1;
+          tc_fence_after();
+          tr.log(l << 8 | 2);
+          if (kStash) {
+            if (stash_leader) bulk_wait_read<0>();  // the previous layer's stash store has read the buffer
+            named_bar_sync(1 + g, 128);
+          }
+        };
+        const bool plain = !is_color && !is_last_trunk;
         if (p.debug & 1) {
-        } else if (is_color)
-          epilogue_half<kFmt, 2, kStash>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
-        else if (is_inter)
-          epilogue_half<kFmt, 1, true>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
-        else
-          epilogue_half<kFmt, 0, true>(t_row, 0, bias, wd, is_last_trunk, dens, w2, acc, act_row, swz);
+          before_store0();
+        } else if (plain) {
+          if (is_inter) epilogue_half_plain<kFmt, false>(t_row, 0, act_row, swz, before_store0);
+          else epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, before_store0);
+        } else {
+          before_store0();
+          if (is_color)
+            epilogue_half<kFmt, 2, kStash>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
+          else
+            epilogue_half<kFmt, 0, true>(t_row, 0, bias, wd, true, dens, w2, acc, act_row, swz);
+        }
         tc_fence_before();
         fence_proxy_async_smem();
         // the last layer feeds no MMA: the next pair's embedding arrival (program order) covers the TMEM hand-over
@@ -460,9 +501,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tr.log(l << 8 | 4);
           if (p.debug & 1) {
           } else if (is_inter)
-            epilogue_half<kFmt, 1, true>(t_row, 128, bias, wd, false, dens, w2, acc, act_row, swz);
+            epilogue_half_plain<kFmt, false>(t_row, 128, act_row, swz, [] {});
+          else if (!is_last_trunk)
+            epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, [] {});
           else
-            epilogue_half<kFmt, 0, true>(t_row, 128, bias, wd, is_last_trunk, dens, w2, acc, act_row, swz);
+            epilogue_half<kFmt, 0, true>(t_row, 128, bias, wd, true, dens, w2, acc, act_row, swz);
           tc_fence_before();
           fence_proxy_async_smem();
         }
