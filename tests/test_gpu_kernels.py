@@ -295,7 +295,8 @@ def _ste_round(x, dt):
 def mlp_forward_operand_rounded(params, spec, origins, directions, lengths, dt):
     """The oracle's `mlp_forward` (nerf_mlp.py:117-177) with the kernel's documented operand rounding inserted:
     embedding, trunk / intermediate weights+biases and every layer output feeding a tensor-core layer are rounded
-    to `dt`; the density head, the per-ray direction bias and the colour head stay fp32."""
+    to `dt` -- including the colour hidden activations and W2 of the colour head, which is a tensor-core layer too;
+    the density head, the per-ray direction bias and the colour head's bias stay fp32."""
     import torch.nn.functional as F
 
     r = lambda t: _ste_round(t, dt)
@@ -312,8 +313,8 @@ def mlp_forward_operand_rounded(params, spec, origins, directions, lengths, dt):
     inter = r(F.linear(y, r(params["intermediate_linear.weight"]), r(params["intermediate_linear.bias"])))
     h = spec.n_hidden_neurons_xyz
     wc = params["color_layer.0.weight"]
-    hid = torch.relu(F.linear(inter, r(wc[:, :h]), None) + (F.linear(demb, wc[:, h:], params["color_layer.0.bias"]))[:, None, :])
-    rgb = torch.sigmoid(F.linear(hid, params["color_layer.2.weight"], params["color_layer.2.bias"]))
+    hid = r(torch.relu(F.linear(inter, r(wc[:, :h]), None) + (F.linear(demb, wc[:, h:], params["color_layer.0.bias"]))[:, None, :]))
+    rgb = torch.sigmoid(F.linear(hid, r(params["color_layer.2.weight"]), params["color_layer.2.bias"]))
     return raw_density, rgb
 
 

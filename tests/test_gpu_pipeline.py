@@ -236,8 +236,12 @@ def test_fused_trainer_converges_like_reference_runner():
     batch = dict(poses=syn.synth_camera(1, seed=0).to(DEV), focal_lengths=torch.full((1, 1), 2.0, device=DEV),
                  image_rgb=torch.rand(1, 2, 2, 3, device=DEV))
     first = None
+    from yanerf.runners.engine import exponential_lr
+
     for it in range(200):
-        preds = trainer.train_step(batch)
+        # the runner's exponential schedule (runners/utils.py:65-109); a constant 5e-3 spikes now and then on this
+        # 4-ray problem, whatever the arithmetic
+        preds = trainer.train_step(batch, lr=exponential_lr(it, 5e-3, 5e-4, 200))
         if first is None:
             first = float(preds["objective"].detach().mean())
     with torch.no_grad():

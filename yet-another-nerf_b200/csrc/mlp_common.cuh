@@ -14,6 +14,8 @@ constexpr int kBlkBytes = 16384;   // one [128 x 64] 16-bit operand block
 constexpr int kMaxLayers = 12;
 constexpr int kDirPad = 128;       // padded width of the colour hidden layer
 constexpr int kBiasBlkBytes = 4096;  // [128 x 16] 16-bit, no swizzle (8x8 core matrices)
+constexpr int kHeadBlkBytes = 4096;  // colour head [16 x 128] 16-bit: two swizzled [16 x 64] sub-blocks
+constexpr int kHeadN = 16;           // UMMA N of the colour head (color_dim <= 3 rows used)
 
 struct Arch {
   int n_layers;
@@ -41,7 +43,10 @@ struct Arch {
     for (int i = 0; i < l; ++i) s += stages(i);
     return s;
   }
-  __host__ __device__ int total_stages() const { return stage_offset(n_mma_layers()); }
+  // after the layers: one 4 KB stage with the colour head, W2 as a [16 x 128] K-major operand (two [16 x 64]
+  // swizzled sub-blocks at byte offsets 0 and 2048; rows >= color_dim are zero)
+  __host__ __device__ int head_stage() const { return stage_offset(n_mma_layers()); }
+  __host__ __device__ int total_stages() const { return head_stage() + 1; }
 
   // true input / output widths of mma layer l
   __host__ __device__ int hidden_in(int l) const {

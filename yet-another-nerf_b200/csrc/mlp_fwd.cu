@@ -114,14 +114,11 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
-// processes accumulator columns [c_lo, c_lo + 128) of one row: (ReLU) -> 16-bit -> activation blocks
-// (c_lo / 64, c_lo / 64 + 1); kMode 0 = trunk (ReLU), 1 = intermediate (no activation), 2 = colour hidden
-// (per-ray direction bias, ReLU, colour head partial sums in `acc`)
-template <int kFmt, int kMode, bool kWrite>
-__device__ __forceinline__ void epilogue_half(uint32_t t_addr, int c_lo, const float* __restrict__ bias,
-                                              const float* __restrict__ wd, bool want_density, float& dens,
-                                              const float* __restrict__ w2, float (&acc)[4], uint32_t act_row,
-                                              uint32_t swz) {
+// last trunk layer: processes accumulator columns [c_lo, c_lo + 128) of one row: ReLU -> 16-bit -> activation blocks
+// (c_lo / 64, c_lo / 64 + 1), and the fp32 density head on the un-rounded activations
+template <int kFmt>
+__device__ __forceinline__ void epilogue_half_density(uint32_t t_addr, int c_lo, const float* __restrict__ wd,
+                                                      float& dens, uint32_t act_row, uint32_t swz) {
 #pragma unroll 1
   for (int cb = 0; cb < 4; cb += 2) {
     uint32_t v[2][32];
@@ -134,44 +131,20 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_addr, int c_lo, const f
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        // trunk / intermediate layers: the bias is already in the accumulator (folded into the MMA)
-        float x0 = __uint_as_float(v[h][j]), x1 = __uint_as_float(v[h][j + 1]);
-        float x2 = __uint_as_float(v[h][j + 2]), x3 = __uint_as_float(v[h][j + 3]);
-        if (kMode == 2) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-          x0 = fmaxf(x0 + b.x, 0.f); x1 = fmaxf(x1 + b.y, 0.f); x2 = fmaxf(x2 + b.z, 0.f); x3 = fmaxf(x3 + b.w, 0.f);
-        }
-        if (kMode == 0 && want_density) {
-          x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-          const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
-          dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
-          dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
-        }
-        if (kMode == 2) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {  // color_dim <= 3
-            const float4 w = __ldg(reinterpret_cast<const float4*>(w2 + c * kDirPad + c0 + j));
-            acc[c] = fmaf(x0, w.x, acc[c]); acc[c] = fmaf(x1, w.y, acc[c]);
-            acc[c] = fmaf(x2, w.z, acc[c]); acc[c] = fmaf(x3, w.w, acc[c]);
-          }
-        }
-        if (kWrite) {
-          if (kMode == 0) {  // ReLU fused into the conversion
-            pk[j / 2] = pack_relu<kFmt>(x0, x1);
-            pk[j / 2 + 1] = pack_relu<kFmt>(x2, x3);
-          } else {
-            pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
-            pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
-          }
-        }
+        // the bias is already in the accumulator (folded into the MMA)
+        const float x0 = fmaxf(__uint_as_float(v[h][j]), 0.f), x1 = fmaxf(__uint_as_float(v[h][j + 1]), 0.f);
+        const float x2 = fmaxf(__uint_as_float(v[h][j + 2]), 0.f), x3 = fmaxf(__uint_as_float(v[h][j + 3]), 0.f);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
+        dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
+        dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
+        pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
+        pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
       }
-      if (kWrite) {
-        const uint32_t blk = act_row + (c0 >> 6) * kBlkBytes;
-        const uint32_t u0 = ((c0 >> 5) & 1) * 4;
+      const uint32_t blk = act_row + (c0 >> 6) * kBlkBytes;
+      const uint32_t u0 = ((c0 >> 5) & 1) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-      }
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
   }
 }
@@ -208,6 +181,34 @@ __device__ __forceinline__ void epilogue_half_plain(uint32_t t_addr, int c_lo, u
   }
 }
 
+// colour hidden layer (128 wide): + per-ray direction bias (LinearWithRepeat's ray half, fp32), ReLU, 16-bit ->
+// activation blocks 0,1 = the A operand of the colour-head MMA
+template <int kFmt>
+__device__ __forceinline__ void epilogue_color_hidden(uint32_t t_addr, const float* __restrict__ dirbias_row,
+                                                      uint32_t act_row, uint32_t swz) {
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {  // one 64-column activation block per iteration
+    uint32_t v[2][32];
+    tmem_ld32(t_addr + cb * 64, v[0]);
+    tmem_ld32(t_addr + cb * 64 + 32, v[1]);
+    tmem_ld_wait();
+    const uint32_t blk = act_row + cb * kBlkBytes;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(dirbias_row + cb * 64 + h * 32 + j));
+        pk[j / 2] = pack_relu<kFmt>(__uint_as_float(v[h][j]) + b.x, __uint_as_float(v[h][j + 1]) + b.y);
+        pk[j / 2 + 1] = pack_relu<kFmt>(__uint_as_float(v[h][j + 2]) + b.z, __uint_as_float(v[h][j + 3]) + b.w);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_shared_v4(blk + (((h * 4 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+  }
+}
+
 template <int kFmt, bool kStash>
 __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -216,10 +217,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
   const uint32_t s_emb = smem_base + kSmemEmb;
   const uint32_t s_ring = smem_base + kSmemRing;
   const uint32_t s_bar = smem_base + kSmemBar;
-  // barriers (8 B each): full[4], empty[4], then per tile g: half_full[g][2], blk01_free[g], epi_done[g][2];
-  // then the TMEM base address
+  // barriers (8 B each): full[4], empty[4], then per tile g: half_full[g][2], blk01_free[g], epi_done[g][2],
+  // next_pair[g]; then the TMEM base address
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kRing, bar_hfull = s_bar + 16 * kRing,
-                 bar_b01 = bar_hfull + 32, bar_epi = bar_b01 + 16, s_tmem_ptr = bar_epi + 32;
+                 bar_b01 = bar_hfull + 32, bar_epi = bar_b01 + 16, bar_next = bar_epi + 32, s_tmem_ptr = bar_next + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       mbar_init(bar_b01 + 8 * g, 1);
       mbar_init(bar_epi + 16 * g, 128);
       mbar_init(bar_epi + 16 * g + 8, 128);
+      mbar_init(bar_next + 8 * g, 128);
     }
     mbar_fence_init();
   }
@@ -272,6 +274,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
             if (++slot == kRing) { slot = 0; phase ^= 1; }
           }
         }
+        // colour head stage (4 KB)
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        if (p.debug & 2) {
+          mbar_arrive(bar_full + 8 * slot);
+        } else {
+          mbar_arrive_expect_tx(bar_full + 8 * slot, kHeadBlkBytes);
+          bulk_g2s(s_ring + slot * kBlkBytes, p.wpack + (size_t)A.head_stage() * kBlkBytes, kHeadBlkBytes, bar_full + 8 * slot);
+        }
+        if (++slot == kRing) { slot = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -287,7 +298,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       const uint32_t my_epi = bar_epi + 16 * g, my_hfull = bar_hfull + 16 * g, my_b01 = bar_b01 + 8 * g;
       const uint32_t act_base = s_act + g * 4 * kBlkBytes, emb_base = s_emb + g * kBlkBytes;
       uint32_t slot = 0, phase = 0;
-      uint32_t ed_phase0 = 0, ed_phase1 = 0;
+      uint32_t ed_phase0 = 0, ed_phase1 = 0, next_phase = 0;
+      const uint32_t my_next = bar_next + 8 * g;
       Tracer tr;
       tr.init(p.trace, g);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -298,8 +310,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           const int kb_free = nkb > 1 ? 1 : 0;
           const bool has_bias = A.has_bias_stage(l);
           tr.log(l << 8 | 0);
-          mbar_wait(my_epi, ed_phase0);
-          ed_phase0 ^= 1;
+          if (l == 0 && pair != (int64_t)blockIdx.x) {
+            // later pairs: "embedding ready, accumulator half 0 drained" comes from the previous pair's colour layer on
+            // its own barrier (a second completion of epi_done[0] right behind the head's could alias its phase)
+            mbar_wait(my_next, next_phase);
+            next_phase ^= 1;
+          } else {
+            mbar_wait(my_epi, ed_phase0);
+            ed_phase0 ^= 1;
+          }
           tc_fence_after();
           tr.log(l << 8 | 1);
           bool waited1 = false;
@@ -342,6 +361,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
             mbar_wait(my_epi + 8, ed_phase1);
             ed_phase1 ^= 1;
           }
+        }
+        // colour head: [128 x 128] hidden activations (blocks 0,1, written by the colour layer's epilogue) x W2^T
+        // -> 16 accumulator columns in the tile's (drained) second half; signalled on the "half 1" barrier
+        {
+          constexpr uint32_t idesc_head = umma_idesc(128, kHeadN, kFmt, 0, 0);
+          tr.log(L << 8 | 0);
+          mbar_wait(my_epi, ed_phase0);
+          ed_phase0 ^= 1;
+          mbar_wait(my_epi + 8, ed_phase1);
+          ed_phase1 ^= 1;
+          tr.log(L << 8 | 1);
+          mbar_wait(bar_full + 8 * slot, phase);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + g * 256 + 128;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t a_desc = umma_desc_kmajor(act_base + kb * kBlkBytes);
+            const uint64_t b_desc = umma_desc_kmajor(s_ring + slot * kBlkBytes + kb * 2048);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_head, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + 8 * slot);
+          if (++slot == kRing) { slot = 0; phase ^= 1; }
+          umma_commit(my_hfull + 8);
+          tr.log(L << 8 | 5);
         }
       }
     }
@@ -436,11 +480,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       }
       // ---- embedding of this tile: computed here for the CTA's first pair, otherwise prefetched during the
       // previous pair (see below)
-      if (pair == (int64_t)blockIdx.x) write_embedding(tile);
-      // the embedding acts as the epilogue of a virtual layer -1: both halves "done"
+      const bool first_pair = pair == (int64_t)blockIdx.x;
+      if (first_pair) write_embedding(tile);
+      // the embedding acts as the epilogue of a virtual layer -1.  "Half 0 done" (embedding written, accumulator
+      // columns [0,128) drained) was already signalled from the previous pair's colour layer, so that layer 0 starts
+      // under the colour head; "half 1 done" (the head's 16 columns have been read) is signalled here.
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(my_epi);
+      if (first_pair) mbar_arrive(my_epi);
       mbar_arrive(my_epi + 8);
       if (kStash) {
         named_bar_sync(1 + g, 128);
@@ -451,14 +498,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       }
 
       float dens = 0.f;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int l = 0; l < L; ++l) {
         const bool is_color = (l == L - 1);
         const bool is_inter = (l == L - 2);
         const bool is_last_trunk = (l == L - 3);
         const float* bias = is_color ? p.dirbias + ray * kDirPad : p.aux + A.aux_bias(l);
         const float* wd = p.aux + A.aux_wd();
-        const float* w2 = p.aux + A.aux_w2();
+        if (is_inter) {  // the colour layer's per-ray bias row (512 B): pull it into L1 one layer ahead
+          const float* row_bias = p.dirbias + ray * kDirPad;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(row_bias + 32 * i));
+        }
         // ---- half 0: accumulator columns [0,128) -> activation blocks 0,1
         tr.log(l << 8 | 0);
         mbar_wait(my_hfull, hf_phase0);
@@ -481,17 +531,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         } else if (plain) {
           if (is_inter) epilogue_half_plain<kFmt, false>(t_row, 0, act_row, swz, before_store0);
           else epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, before_store0);
+        } else if (is_color) {
+          before_store0();
+          epilogue_color_hidden<kFmt>(t_row, bias, act_row, swz);
         } else {
           before_store0();
-          if (is_color)
-            epilogue_half<kFmt, 2, kStash>(t_row, 0, bias, wd, false, dens, w2, acc, act_row, swz);
-          else
-            epilogue_half<kFmt, 0, true>(t_row, 0, bias, wd, true, dens, w2, acc, act_row, swz);
+          epilogue_half_density<kFmt>(t_row, 0, wd, dens, act_row, swz);
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        // the last layer feeds no MMA: the next pair's embedding arrival (program order) covers the TMEM hand-over
-        if (!is_color) mbar_arrive(my_epi);
+        mbar_arrive(my_epi);
         tr.log(l << 8 | 3);
         // ---- half 1: columns [128,256) -> blocks 2,3 (the colour hidden layer is 128 wide: nothing to do)
         if (!is_color) {
@@ -505,12 +554,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           else if (!is_last_trunk)
             epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, [] {});
           else
-            epilogue_half<kFmt, 0, true>(t_row, 128, bias, wd, true, dens, w2, acc, act_row, swz);
+            epilogue_half_density<kFmt>(t_row, 128, wd, dens, act_row, swz);
           tc_fence_before();
           fence_proxy_async_smem();
         }
-        if (!is_color) mbar_arrive(my_epi + 8);
+        mbar_arrive(my_epi + 8);  // (colour layer: blocks 0,1 hold the hidden activations, the head MMA may start)
         tr.log(l << 8 | 5);
+        if (is_color && pair + gridDim.x < n_pairs) {
+          // next pair, layer 0, half 0 may start right behind the head MMA: its embedding was prefetched and
+          // accumulator columns [0,128) are drained
+          mbar_arrive(bar_next + 8 * g);
+        }
         if (l == l_emb_last && pair + gridDim.x < n_pairs) {
           // every MMA that reads this tile's embedding as an operand has completed (half_full[1] of this layer):
           // prefetch the next pair's embedding now, in the shadow of the remaining layers.  Later bias MMAs read
@@ -522,11 +576,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           write_embedding(2 * (pair + gridDim.x) + g);
         }
         if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
-        if (is_color && valid) {
-          const int C = A.color_dim;
-          for (int c = 0; c < C; ++c) {
-            const float x = acc[c] + __ldg(p.aux + A.aux_b2() + c);
-            p.rgb[gidx * C + c] = 1.f / (1.f + expf(-x));
+        if (is_color) {
+          // colour head: 16 accumulator columns at the start of the tile's second half (the first color_dim are real);
+          // the next pair's embedding arrival (program order) covers the TMEM hand-over
+          mbar_wait(my_hfull + 8, hf_phase1);
+          hf_phase1 ^= 1;
+          tc_fence_after();
+          uint32_t hv[4];
+          tmem_ld4(t_row + 128, hv);
+          tmem_ld_wait();
+          tr.log(L << 8 | 4);
+          if (valid) {
+            const int C = A.color_dim;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              if (c < C) {
+                const float x = __uint_as_float(hv[c]) + __ldg(p.aux + A.aux_b2() + c);
+                p.rgb[gidx * C + c] = 1.f / (1.f + expf(-x));
+              }
           }
         }
         if (kStash) {

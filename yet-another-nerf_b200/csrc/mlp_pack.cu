@@ -30,6 +30,27 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
     // forward block (l, nh, kb): rows = output features nh*128 + r, cols = input columns of K-block kb
     int l = 0, off = 0;
     while (l < L && s >= off + A.stages(l)) { off += A.stages(l); ++l; }
+    if (l == L) {
+      // colour head stage: W2 [color_dim x hidden_dir] as a [16 x 128] K-major operand, sub-block kb at kb * 2048
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      size_t dst = (size_t)unit * 16;
+      if (unit < 256) {
+        const int kb = unit >> 7, rr = (unit >> 3) & 15, uu = unit & 7;
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = kb * 64 + uu * 8 + i;
+          w[i] = (rr < A.color_dim && k < A.hidden_dir) ? params[A.color2_w_offset() + (int64_t)rr * A.hidden_dir + k] : 0.f;
+        }
+        out.x = Half2Pack<kFmt>::pack(w[0], w[1]);
+        out.y = Half2Pack<kFmt>::pack(w[2], w[3]);
+        out.z = Half2Pack<kFmt>::pack(w[4], w[5]);
+        out.w = Half2Pack<kFmt>::pack(w[6], w[7]);
+        dst = (size_t)kb * 2048 + rr * 128 + ((uu ^ (rr & 7)) << 4);
+      }
+      *reinterpret_cast<uint4*>(wpack + (size_t)s * kBlkBytes + dst) = out;
+      return;
+    }
     const int local = s - off;
     const int nkb = A.nkb(l);
     const int per_half = A.stages_per_half(l);
