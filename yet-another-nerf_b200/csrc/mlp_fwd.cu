@@ -343,8 +343,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
                 umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
               umma_commit(bar_empty + 8 * slot);
               if (++slot == kRing) { slot = 0; phase ^= 1; }
-              // activation blocks 0,1 are not read again in this layer after (last half, kb_free)
-              if (nh == nnh - 1 && kb == kb_free) umma_commit(my_b01);
+              // activation blocks 0,1 are not read again in this layer after (last half, kb_free); layer 0 reads
+              // only the embedding block, so they are free from its first MMA on
+              if (l == 0 ? (nh == 0 && kb == 0) : (nh == nnh - 1 && kb == kb_free)) umma_commit(my_b01);
             }
             if (has_bias) {
               // + bias: embedding slice 3 (channel 63 == 1) x the [128 x 16] bias block
