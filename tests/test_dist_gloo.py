@@ -77,3 +77,44 @@ def test_two_rank_flat_allreduce_matches_single_process(tmp_path):
             grads.append(torch.cat([p.grad.reshape(-1) for p in params]))
         O.adam_step(flat, (grads[0] + grads[1]) * 0.5, m, v, s + 1, 1e-2)
     torch.testing.assert_close(r0["flat"], flat, rtol=1e-6, atol=1e-7)
+
+
+def _slab_worker(rank, world, port, tmp):
+    for p in (REPO, os.path.join(REPO, "yet-another-nerf_b200")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from yanerf.pipelines.nerf_pipeline import gather_slabs, slab_bounds
+
+    n_rays, B = 1000, 2  # not a multiple of the 128-ray alignment: the last slab is short
+    full = torch.arange(B * n_rays * 5, dtype=torch.float32).reshape(B, n_rays, 5)
+    s, e, per = slab_bounds(n_rays, world, rank)
+    out = gather_slabs(full[:, s:e].clone(), n_rays, per)
+    torch.save({"out": out, "bounds": (s, e, per)}, os.path.join(tmp, f"s{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_ray_slab_partition_and_gather(tmp_path):
+    """SURVEY 8(e) render sharding: contiguous, tile-aligned slabs that cover every ray once; the all-gather rebuilds
+    the full ray list on every rank (world 2, gloo)."""
+    for p in (REPO, os.path.join(REPO, "yet-another-nerf_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from yanerf.pipelines.nerf_pipeline import slab_bounds
+
+    for n_rays, world in ((640000, 8), (190512, 4), (1000, 2), (100, 4), (129, 3)):
+        covered = 0
+        for r in range(world):
+            s, e, per = slab_bounds(n_rays, world, r)
+            assert s == min(r * per, n_rays) and s <= e <= n_rays and per % 128 == 0
+            assert s == covered or s == n_rays
+            covered = max(covered, e)
+        assert covered == n_rays
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_slab_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    full = torch.arange(2 * 1000 * 5, dtype=torch.float32).reshape(2, 1000, 5)
+    for r in range(2):
+        got = torch.load(tmp_path / f"s{r}.pt")
+        assert torch.equal(got["out"], full)
+    assert torch.load(tmp_path / "s0.pt")["bounds"] == (0, 512, 512)
+    assert torch.load(tmp_path / "s1.pt")["bounds"] == (512, 1000, 512)

@@ -389,3 +389,35 @@ def test_cuda_graph_training_matches_eager_and_converges():
     print("eager", le, pe, "graph", lg, pg)
     assert pe > 22.0 and pg > 22.0
     assert abs(pe - pg) < 4.0  # different random pixel / jitter draws, same optimisation
+
+
+def test_ray_slab_sharded_render_equals_unsharded(monkeypatch):
+    """rendering one image as 3 ray slabs (one per emulated rank) and stitching the slabs gives the
+    same image, bit for bit, as the unsharded render: rays are independent and slabs are whole MLP tiles."""
+    import yanerf.pipelines.nerf_pipeline as NP
+
+    H, W = 50, 44  # 2200 rays -> slabs of 768, 768, 664
+    pipe = build_pipeline(H, W, 256, 64, 0.0, 4096).to(DEV)
+    load_synth_nets(pipe, seeds=(3, 4), gain=1.0)
+    batch = dict(poses=syn.synth_camera(1, seed=2).to(DEV), focal_lengths=torch.full((1, 1), 60.0, device=DEV),
+                 image_rgb=syn.synth_image(1, H, W, seed=3).to(DEV))
+    with torch.no_grad():
+        ref = pipe(**batch, evaluation_mode=EvaluationMode.EVALUATION)
+        acc = {}
+
+        def fake_gather(local, n_rays, per, group=None):
+            rank = pipe.ray_shard[0]
+            full = local.new_zeros(local.shape[0], n_rays, local.shape[2])
+            s = min(rank * per, n_rays)
+            full[:, s:s + local.shape[1]] = local
+            return full
+
+        monkeypatch.setattr(NP, "gather_slabs", fake_gather)
+        for rank in range(3):
+            pipe.ray_shard = (rank, 3, None)
+            out = pipe(**batch, evaluation_mode=EvaluationMode.EVALUATION)
+            for k in ("rendered_images", "rendered_depths", "rendered_alpha_masks"):
+                acc[k] = out[k] if k not in acc else acc[k] + out[k]
+        pipe.ray_shard = None
+    for k, v in acc.items():
+        assert torch.equal(v, ref[k]), k

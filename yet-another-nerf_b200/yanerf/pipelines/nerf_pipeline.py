@@ -50,6 +50,36 @@ def _chunk_generator(chunk_size: int, origins, directions, lengths, xys, bg_colo
         yield [o[:, s:e], d[:, s:e], z[:, s:e], xy[:, s:e], None if bg is None else bg[:, s:e], *args], kwargs
 
 
+# ---------------------------------------------------------------------------------------------- ray-slab sharding
+# one image over several GPUs.  The flattened H*W ray list is cut into `world` contiguous slabs (a multiple
+# of 128 rays, so every slab is a whole number of MLP tiles for any points-per-ray count), every rank renders its slab
+# with the replicated weights, then ONE all-gather of `[B, slab, 5]` fp32 per renderer stage (rgb, depth, alpha)
+# rebuilds the image on every rank.  No exchange inside a ray.
+SLAB_ALIGN = 128
+
+
+def slab_bounds(n_rays: int, world: int, rank: int, align: int = SLAB_ALIGN):
+    """(start, end, rays per slab) of rank's slab; the last slabs may be short or empty."""
+    per = -(-n_rays // world)
+    per = -(-per // align) * align
+    start = min(rank * per, n_rays)
+    return start, min(start + per, n_rays), per
+
+
+def gather_slabs(local: torch.Tensor, n_rays: int, per: int, group=None) -> torch.Tensor:
+    """`[B, n_local, C]` (this rank's slab) -> `[B, n_rays, C]` on every rank."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local[:, :n_rays]
+    world = dist.get_world_size(group)
+    B, n_local, C = local.shape
+    padded = local if n_local == per else torch.cat((local, local.new_zeros(B, per - n_local, C)), dim=1)
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat(parts, dim=1)[:, :n_rays]
+
+
 def _tensor_collator(batch, new_dims) -> torch.Tensor:
     """`[B, rays_i, 1, *rest]` pieces -> `[*new_dims, *rest]`."""
     rest = batch[0].shape[3:]
@@ -89,6 +119,9 @@ class NeRFPipeline(torch.nn.Module):
     # True = the reference's per-call range assertions on the pixel grid (device->host syncs).  FusedTrainer turns
     # it off: a grid produced by this pipeline's own ray sampler is checked against the image size on the host.
     validate_pixel_grid: bool = True
+    # (rank, world, process group) -> full-grid renders are ray-slab sharded over the group (see slab_bounds); None =
+    # every rank renders whole images (the reference's DistributedSampler sharding)
+    ray_shard: Optional[tuple] = None
 
     def __init__(
         self,
@@ -220,6 +253,35 @@ class NeRFPipeline(torch.nn.Module):
         return preds
 
     def _render(self, origins, directions, lengths, xys, *, bg_color, sampling_mode, **kwargs) -> RendererOutput:
+        if sampling_mode == RenderSamplingMode.FULL_GRID and self.ray_shard is not None:
+            return self._render_sharded(origins, directions, lengths, xys, bg_color=bg_color, sampling_mode=sampling_mode,
+                                        **kwargs)
+        return self._render_local(origins, directions, lengths, xys, bg_color=bg_color, sampling_mode=sampling_mode,
+                                  **kwargs)
+
+    def _render_sharded(self, origins, directions, lengths, xys, *, bg_color, **kwargs) -> RendererOutput:
+        rank, world, group = self.ray_shard
+        B, *spatial, P = lengths.shape
+        n_rays = math.prod(spatial)
+        start, end, per = slab_bounds(n_rays, world, rank)
+        flat = lambda t: None if t is None else t.reshape(B, n_rays, 1, t.shape[-1])[:, start:end]
+        stages = []
+        if end > start:
+            out = self._render_local(flat(origins), flat(directions), flat(lengths), flat(xys), bg_color=flat(bg_color),
+                                     **kwargs)
+            while out is not None:
+                stages.append(torch.cat((out.features, out.depths, out.alpha_masks), dim=-1).reshape(B, end - start, -1))
+                out = out.prev_stage
+        else:  # more ranks than slabs: contribute an empty slab per stage
+            stages = [lengths.new_zeros(B, 0, 5) for _ in range(self.num_passes)]
+        result = None
+        for packed in reversed(stages):  # coarsest stage first, so that prev_stage chains like the renderer's output
+            full = gather_slabs(packed, n_rays, per, group).reshape(B, *spatial, packed.shape[-1])
+            result = RendererOutput(features=full[..., :-2], depths=full[..., -2:-1], alpha_masks=full[..., -1:],
+                                    prev_stage=result)
+        return result
+
+    def _render_local(self, origins, directions, lengths, xys, *, bg_color, sampling_mode, **kwargs) -> RendererOutput:
         if sampling_mode == RenderSamplingMode.FULL_GRID and self.chunk_size_grid > 0:
             chunk = self.chunk_size_grid
             if self.coalesce_chunks:

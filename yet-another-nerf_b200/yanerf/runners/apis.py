@@ -40,6 +40,16 @@ def concat_all_gather(t: torch.Tensor) -> torch.Tensor:
     return torch.cat(parts, dim=0)
 
 
+def enable_ray_sharding(model: torch.nn.Module, group=None) -> bool:
+    """SURVEY 8(e), render: from now on every full-grid render of `model` is split into contiguous ray slabs over the
+    ranks of `group` and re-assembled with one all-gather per renderer stage (`NeRFPipeline.ray_shard`).  All ranks must
+    then call the model with the SAME image.  Returns False (and changes nothing) without a multi-rank process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return False
+    model.ray_shard = (dist.get_rank(group), dist.get_world_size(group), group)
+    return True
+
+
 def train_one_epoch(trainer: FusedTrainer, batches: Iterable[Dict[str, Any]], config: Dict[str, Any], epoch: int = 0,
                     iters_per_epoch: Optional[int] = None) -> Dict[str, float]:
     """One pass over `batches` (dicts of device tensors keyed like the dataset NamedTuples)."""
