@@ -32,9 +32,10 @@ class FusedTrainer:
 
     def __init__(self, pipeline: torch.nn.Module, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  process_group: Optional[Any] = None, use_cuda_graph: bool = False, graph_warmup_steps: int = 3) -> None:
-        """use_cuda_graph: after `graph_warmup_steps` eager steps the whole iteration (pixel pick, forward, backward,
-        all-reduce, Adam, weight re-pack) is captured once and replayed; step counter, learning rate and the pixel
-        seed live in device memory so every replay sees fresh values."""
+        """use_cuda_graph: after `graph_warmup_steps` eager steps the whole iteration (pixel pick, weight re-pack,
+        forward, backward, Adam) is captured once and replayed; step counter, learning rate and the pixel seed live in
+        device memory so every replay sees fresh values.  With several ranks the NCCL all-reduce and Adam follow the
+        replay as ordinary launches."""
         self.pipeline = pipeline
         self.use_cuda_graph = use_cuda_graph
         self._graph_warmup = graph_warmup_steps
@@ -147,6 +148,9 @@ class FusedTrainer:
                 self._static_batch[k].copy_(v, non_blocking=True)
         self._state[1:2].copy_(self._lr_host, non_blocking=True)
         self._graph.replay()  # (the captured forward starts by re-packing the weight images from the flat buffer)
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self._graph_optimizer()
         self.step_count += 1
         self._invalidate()    # other weight images (e.g. the fp16 one used by evaluation) are stale now
         self._deferred_checks()
@@ -164,12 +168,17 @@ class FusedTrainer:
             if "objective" not in preds:
                 raise KeyError("objective")
             preds["objective"].mean().backward()
-            if self.world > 1:
-                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self._state[0:1] += 1.0
-            ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._state, self.betas[0],
-                              self.betas[1], self.eps, grad_scale=1.0 / self.world)
+            if self.world == 1:
+                self._graph_optimizer()
             self._static_preds = {k: v.detach() if torch.is_tensor(v) else v for k, v in preds.items()}
+
+    def _graph_optimizer(self) -> None:
+        """Adam with step count / learning rate read from device memory.  Single GPU: part of the captured graph.
+        Multi-GPU: launched after the replay, behind the NCCL all-reduce (NCCL stays outside the capture: its
+        watchdog and the capture do not mix reliably)."""
+        self._state[0:1] += 1.0
+        ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._state, self.betas[0],
+                          self.betas[1], self.eps, grad_scale=1.0 / self.world)
 
     def _deferred_checks(self) -> None:
         """The refiner's device flag of step k is copied to pinned memory asynchronously and examined at the end of
