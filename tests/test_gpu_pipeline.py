@@ -370,6 +370,7 @@ def test_cuda_graph_training_matches_eager_and_converges():
         cfg.ray_sampler.n_pts_per_ray_evaluation = 32
         pipe = PIPELINES.build(cfg).to(DEV)
         trainer = FusedTrainer(pipe, lr=5e-4, use_cuda_graph=graph)
+        assert pipe.ray_sampler.fused_pixel_sampler  # the trainer switches the O(n) on-device pixel pick on
         batch = dict(poses=syn.synth_camera(1, seed=0, jitter=0.0).to(DEV), focal_lengths=torch.full((1, 1), 30.0, device=DEV),
                      image_rgb=img[None].to(DEV))
         losses = []

@@ -590,7 +590,12 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
       for (int c = 0; c < 3; ++c) s_red[rg][kInner + c * kDirPad + u * 8 + i] = acc_w2[c][i];
   }
   __syncthreads();
-  for (int j = t; j < kInner + 3 * kDirPad; j += blockDim.x) {
+  // every block adds to the same 640 addresses at about the same time: start each block at a different offset so that
+  // concurrent atomics land on different addresses (same-address atomics serialise in L2)
+  constexpr int kFlush = kInner + 3 * kDirPad;
+  const int rot = (int)((blockIdx.x * 83u) % kFlush);
+  for (int j0 = t; j0 < kFlush; j0 += blockDim.x) {
+    const int j = j0 + rot < kFlush ? j0 + rot : j0 + rot - kFlush;
     float v = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) v += s_red[g][j];
@@ -664,7 +669,10 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
   __syncthreads();
   const int din = A.din(n + 1);
   float* W = p.grads + A.w_offset(n + 1);
-  for (int i = threadIdx.x; i < A.hidden_dir * ed; i += blockDim.x) {
+  const int n_flush = A.hidden_dir * ed;
+  const int rot = (int)((blockIdx.x * 331u) % (unsigned)n_flush);  // de-correlate the blocks' atomics (see heads kernel)
+  for (int i0 = threadIdx.x; i0 < n_flush; i0 += blockDim.x) {
+    const int i = i0 + rot < n_flush ? i0 + rot : i0 + rot - n_flush;
     const int j = i / ed, k = i % ed;
     atomicAdd(W + (int64_t)j * din + A.hidden_last + k, s_acc[j * 28 + k]);
   }

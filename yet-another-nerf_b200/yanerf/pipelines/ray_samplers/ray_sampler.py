@@ -194,6 +194,16 @@ class RaySampler(torch.nn.Module):
         self.register_buffer("scene_center", torch.tensor(scene_center, dtype=torch.float32), persistent=False)
         self.scene_extent = scene_extent
 
+    @property
+    def fused_pixel_sampler(self) -> bool:
+        """Unmasked pixel picks through `yn_sample_pixels` instead of torch.multinomial (see _RaySampler)."""
+        return all(s.fused_pixel_sampler for s in self._raysamplers.values())
+
+    @fused_pixel_sampler.setter
+    def fused_pixel_sampler(self, value: bool) -> None:
+        for s in self._raysamplers.values():  # plain dict, not sub-modules: `.modules()` does not reach them
+            s.fused_pixel_sampler = bool(value)
+
     def forward(self, poses, focal_lengths, evaluation_mode: EvaluationMode, *, mask=None, sampling_prob_mask=None,
                 image_height=None, image_width=None, min_depth=None, max_depth=None,
                 n_rays_per_image: Union[None, int, List[int]] = None) -> RayBundle:
