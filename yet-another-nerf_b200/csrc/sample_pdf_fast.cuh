@@ -90,37 +90,38 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_fast_kernel(const PdfPar
     for (int j = 0; j < 8; ++j) total = __fadd_rn(total, __shfl_sync(0xffffffffu, part, j));
   }
 
-  // ---- pdf, cdf (fp64 running sum rounded per prefix); lane i owns k = PS*i .. PS*i + PS - 1
+  // ---- pdf, cdf; lane i owns k = PS*i .. PS*i + PS - 1.
+  // torch.cumsum on the CPU accumulates in fp64 and rounds every prefix to fp32.  As long as every pdf value is
+  // >= 2^-28 (always inside the renderer: w + 1e-5 >= 1e-5, total <= P), each addend's lowest mantissa bit is
+  // >= 2^-51 and every partial sum is < 2, so the fp64 sums are EXACT -- and a 64-bit fixed-point sum (2^-62
+  // resolution) reproduces them bit for bit in any association order, on the integer pipe (fp64 runs at a few lanes
+  // per clock on this part and dominated the kernel).  Rows with a smaller value take the sequential fp64 redo below.
   float pdf[PS];
-  double pre[PS], run = 0.0;
+  unsigned long long pre[PS], run = 0ull;
+  bool ambiguous = false;
 #pragma unroll
   for (int r = 0; r < PS; ++r) {
     const int k = lane * PS + r;
     pdf[r] = k < K ? __fdiv_rn(wp[k], total) : 0.f;
-    run += static_cast<double>(pdf[r]);
+    if (k < K) {
+      const bool fits = pdf[r] >= 0x1p-28f && pdf[r] < 2.f;  // (false for NaN)
+      ambiguous |= !fits;
+      run += fits ? __float2ull_rz(__fmul_rn(pdf[r], 0x1p62f)) : 0ull;  // exact: a power-of-two scaling
+    }
     pre[r] = run;
   }
-  double incl = run;
+  unsigned long long incl = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) excl = 0.0;
-  bool ambiguous = false;
+  unsigned long long excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 0ull;
+  ambiguous |= incl >= (1ull << 63);  // cannot happen for a normalised pdf; keeps the fixed point honest
   float cdfv[PS];
 #pragma unroll
-  for (int r = 0; r < PS; ++r) {
-    const double d = excl + pre[r];
-    const float f = static_cast<float>(d);
-    cdfv[r] = f;
-    // distance of d to the two fp32 rounding boundaries around f (f > 0): neighbours by bit pattern
-    const uint32_t b = __float_as_uint(f);
-    const double mid_up = 0.5 * (static_cast<double>(f) + static_cast<double>(__uint_as_float(b + 1)));
-    const double mid_dn = 0.5 * (static_cast<double>(f) + static_cast<double>(__uint_as_float(b - 1)));
-    if (lane * PS + r < K) ambiguous |= (mid_up - d < 4e-14 * d) || (d - mid_dn < 4e-14 * d);
-  }
+  for (int r = 0; r < PS; ++r) cdfv[r] = __fmul_rn(__ull2float_rn(excl + pre[r]), 0x1p-62f);  // RNE like fp64 -> fp32
   __syncwarp();  // every lane has consumed its wp[] before they are overwritten
 #pragma unroll
   for (int r = 0; r < PS; ++r) {
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_fast_kernel(const PdfPar
   for (int i = NB + lane; i < CDFN; i += 32) s_cdf[i] = CUDART_INF_F;
   __syncwarp();
   if (__any_sync(0xffffffffu, ambiguous)) {
-    if (lane == 0) {  // exact sequential redo (practically never taken)
+    if (lane == 0) {  // sequential fp64 redo = torch's own order (never taken inside the renderer)
       double acc = 0.0;
       for (int k = 0; k < K; ++k) {
         const float wv = __fadd_rn(__ldg(wr + k + 1), 1e-5f);
