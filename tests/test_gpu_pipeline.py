@@ -422,3 +422,52 @@ def test_ray_slab_sharded_render_equals_unsharded(monkeypatch):
         pipe.ray_shard = None
     for k, v in acc.items():
         assert torch.equal(v, ref[k]), k
+
+
+def test_checkpoint_resume_continues_the_same_trajectory():
+    """save in the reference's checkpoint layout after 4 steps, load into a fresh pipeline + trainer,
+    continue 3 steps: same weights as the uninterrupted run (up to the fp32 atomics of the gradient reduction)."""
+    import io
+
+    from yanerf.pipelines import PIPELINES
+    from yanerf.runners import FusedTrainer
+
+    H = W = 16
+    batch = dict(poses=syn.synth_camera(1, seed=0, jitter=0.0).to(DEV), focal_lengths=torch.full((1, 1), 20.0, device=DEV),
+                 image_rgb=syn.synth_image(1, H, W, seed=5).to(DEV))
+
+    def fresh():
+        torch.manual_seed(11)
+        cfg = pipeline_cfg(H, W, 128, 32, 0.0, chunk=131072)
+        cfg.ray_sampler.n_pts_per_ray_training = 32
+        pipe = PIPELINES.build(cfg).to(DEV)
+        return pipe, FusedTrainer(pipe, lr=1e-3)
+
+    def reseed(pipe):
+        for smp in pipe.ray_sampler._raysamplers.values():
+            smp._pixel_seed = None  # drawn from torch's CPU generator at the next pick
+        torch.manual_seed(99)
+
+    pipe_a, tr_a = fresh()
+    for _ in range(4):
+        tr_a.train_step(batch)
+    buf = io.BytesIO()
+    torch.save(tr_a.state_dict(epoch=0), buf)  # the file scripts/run.py:416-422 writes
+    reseed(pipe_a)
+    for _ in range(3):
+        tr_a.train_step(batch)
+    tr_a.finish()
+
+    pipe_b, tr_b = fresh()
+    buf.seek(0)
+    assert tr_b.load_state_dict(torch.load(buf, map_location="cpu")) == 1
+    assert tr_b.step_count == 4
+    reseed(pipe_b)
+    for _ in range(3):
+        tr_b.train_step(batch)
+    tr_b.finish()
+    assert tr_b.step_count == 7
+    diff = float((tr_a.flat - tr_b.flat).abs().max())
+    moved = float((tr_a.flat - fresh()[1].flat).abs().max())
+    print("resume: max |dW| between runs", diff, "vs distance travelled", moved)
+    assert diff <= 2e-4 * max(moved, 1e-3) + 1e-6

@@ -188,3 +188,70 @@ def test_lr_schedule_and_stats():
     assert abs(exponential_lr(500, 5e-4, 5e-5, 200000, warmup_iters=1000, warmup_lr=1e-5) - (1e-5 + 4.9e-4 * 0.5)) < 1e-12
     st = create_stats({"loss_rgb_mse": torch.tensor([0.01, 0.01]), "objective": torch.tensor([0.5]), "rendered_images": torch.zeros(1)})
     assert abs(st["loss_rgb_psnr"] - 20.0) < 1e-4 and st["objective"] == 0.5 and "rendered_images" not in st
+
+
+# --------------------------------------------------------------------------- checkpoint wire format
+def _ckpt_layout():
+    import json
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "checkpoint_layout.json")))
+
+
+def test_state_dict_keys_and_parameter_order_match_reference_checkpoint():
+    """tests/golden/checkpoint_layout.json is the layout of a checkpoint written by the REFERENCE
+    (scripts/run.py:416-422) for the lego pipeline: same state-dict keys, order and shapes here, and the same
+    `parameters()` order, because torch.optim.Adam's state is indexed by parameter position."""
+    from yanerf.testing import build_pipeline
+
+    layout = _ckpt_layout()
+    pipe = build_pipeline(8, 8, 16, 8, 0.0, 4096)
+    mine = [[k, list(v.shape)] for k, v in pipe.state_dict().items()]
+    assert mine == layout["model_keys"]
+    assert [n for n, _ in pipe.named_parameters()] == layout["parameter_order"]
+
+
+def test_fused_trainer_reads_and_writes_reference_checkpoints():
+    """A checkpoint in the reference's layout (model + torch.optim.Adam state + epoch) resumes in FusedTrainer, and
+    what FusedTrainer writes loads into a real torch.optim.Adam over the same module."""
+    from yanerf.runners import FusedTrainer
+    from yanerf.testing import build_pipeline
+
+    layout = _ckpt_layout()
+    torch.manual_seed(3)
+    src = build_pipeline(8, 8, 16, 8, 0.0, 4096)
+    opt = torch.optim.Adam(src.parameters(), lr=3e-4)  # a real Adam state: two steps on random gradients
+    for _ in range(2):
+        for p in src.parameters():
+            p.grad = torch.randn_like(p)
+        opt.step()
+    ckpt = {"model": {k: v.clone() for k, v in src.state_dict().items()}, "optimizer": opt.state_dict(), "epoch": 7}
+    # the synthetic checkpoint has the structure recorded from the reference
+    assert set(ckpt["optimizer"]["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+    assert sorted(ckpt["optimizer"]["state"][0]) == sorted(layout["optimizer"]["state"]["0"])
+
+    dst = build_pipeline(8, 8, 16, 8, 0.0, 4096)
+    trainer = FusedTrainer(dst, lr=1.0)
+    assert trainer.load_state_dict(ckpt) == 8  # resume epoch (run.py:176)
+    assert trainer.step_count == 2 and trainer.lr == 3e-4
+    for (n, p), q in zip(dst.named_parameters(), src.parameters()):
+        assert torch.equal(p, q), n
+        assert p.data_ptr() >= trainer.flat.data_ptr()  # still a view into the flat buffer
+    off = 0
+    for i, p in enumerate(src.parameters()):
+        k = p.numel()
+        assert torch.equal(trainer.exp_avg[off:off + k].view_as(p), opt.state[p]["exp_avg"])
+        assert torch.equal(trainer.exp_avg_sq[off:off + k].view_as(p), opt.state[p]["exp_avg_sq"])
+        off += k
+    # and back: the checkpoint FusedTrainer writes is a valid torch.optim.Adam state for the same module
+    out = trainer.state_dict(epoch=8)
+    assert out["epoch"] == 8 and list(out["model"]) == [k for k, _ in layout["model_keys"]]
+    again = torch.optim.Adam(build_pipeline(8, 8, 16, 8, 0.0, 4096).parameters(), lr=1.0)
+    again.load_state_dict(out["optimizer"])
+    assert again.param_groups[0]["lr"] == 3e-4
+    for i, st in again.state_dict()["state"].items():
+        assert float(st["step"]) == 2.0
+        assert torch.equal(st["exp_avg"], ckpt["optimizer"]["state"][i]["exp_avg"])
+    # a checkpoint for a different architecture fails loudly
+    bad = {"model": ckpt["model"], "optimizer": {"state": {}, "param_groups": [{"params": [0, 1]}]}}
+    with pytest.raises(ValueError, match="optimizer state for 2 parameters"):
+        trainer.load_state_dict(bad)

@@ -218,17 +218,67 @@ class FusedTrainer:
             self._state[0:1].fill_(float(self.step_count))  # keep the graph's device-side step counter in sync
         self._invalidate()
 
-    # checkpoint format of scripts/run.py:416-422 (model state_dict + optimizer state + epoch)
-    def state_dict(self) -> Dict[str, Any]:
-        return {"model": self.pipeline.state_dict(), "optimizer": {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                                                                    "step": self.step_count}}
+    # ------------------------------------------------------------------ checkpoints (scripts/run.py:168-178, 416-422)
+    # Wire format of the reference: {"model": pipeline.state_dict(), "optimizer": torch.optim.Adam.state_dict(),
+    # "epoch": e}.  The optimizer state is indexed by parameter position in `model.parameters()` order, which is the
+    # order of `self.params`; the moments are views into the flat buffers on the way out and copied in on the way in, so a
+    # reference checkpoint resumes here and a checkpoint written here resumes in the reference.
+    def optimizer_state_dict(self) -> Dict[str, Any]:
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off:off + k].view_as(p), "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
+            off += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state if self.step_count > 0 else {}, "param_groups": [group]}
 
-    def load_state_dict(self, state: Dict[str, Any]) -> None:
-        self.pipeline.load_state_dict(state["model"])
-        opt = state.get("optimizer")
-        if opt:
+    def load_optimizer_state_dict(self, opt: Dict[str, Any]) -> None:
+        if "param_groups" not in opt:  # round-1 private layout {"exp_avg", "exp_avg_sq", "step"}
             self.exp_avg.copy_(opt["exp_avg"])
             self.exp_avg_sq.copy_(opt["exp_avg_sq"])
             self.step_count = int(opt["step"])
-            self._state[0:1].fill_(float(self.step_count))
+            return
+        groups = opt["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError(f"optimizer state for {len(order)} parameters, the pipeline has {len(self.params)}")
+        if groups[0].get("weight_decay", 0) or groups[0].get("amsgrad", False):
+            raise NotImplementedError("weight_decay / amsgrad checkpoints (the reference trains with plain Adam, run.py:159)")
+        self.lr = float(groups[0].get("lr", self.lr))
+        self.betas = tuple(groups[0].get("betas", self.betas))
+        self.eps = float(groups[0].get("eps", self.eps))
+        state, off, steps = opt.get("state", {}), 0, set()
+        for pos, p in zip(order, self.params):
+            k = p.numel()
+            st = state.get(pos, state.get(str(pos)))
+            if st is None:  # a parameter that never received a gradient
+                self.exp_avg[off:off + k].zero_()
+                self.exp_avg_sq[off:off + k].zero_()
+            else:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {pos}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+                self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            off += k
+        if len(steps) > 1:
+            raise NotImplementedError(f"per-parameter step counts differ: {sorted(steps)}")
+        self.step_count = steps.pop() if steps else 0
+
+    def state_dict(self, epoch: Optional[int] = None) -> Dict[str, Any]:
+        out = {"model": self.pipeline.state_dict(), "optimizer": self.optimizer_state_dict()}
+        if epoch is not None:
+            out["epoch"] = epoch
+        return out
+
+    def load_state_dict(self, state: Dict[str, Any]) -> int:
+        """Loads a checkpoint in the reference's layout; returns the epoch to resume from (run.py:176)."""
+        self.pipeline.load_state_dict(state["model"])  # copies into the flat-buffer views
+        if state.get("optimizer"):
+            self.load_optimizer_state_dict(state["optimizer"])
+        self._state[0:1].fill_(float(self.step_count))
         self._invalidate()
+        return int(state.get("epoch", -1)) + 1
