@@ -471,3 +471,34 @@ def test_checkpoint_resume_continues_the_same_trajectory():
     moved = float((tr_a.flat - fresh()[1].flat).abs().max())
     print("resume: max |dW| between runs", diff, "vs distance travelled", moved)
     assert diff <= 2e-4 * max(moved, 1e-3) + 1e-6
+
+
+def test_runner_epoch_loop_on_device_feed():
+    """Runner loop end to end (runners/apis.py train_one_epoch / eval_one_epoch) fed by the device-resident scene
+    cache, graph-captured step: the loss of a 6-view synthetic scene falls and the eval stats come out per key."""
+    from yanerf.pipelines import PIPELINES
+    from yanerf.runners import DeviceSceneFeed, FusedTrainer
+    from yanerf.runners.apis import eval_one_epoch, train_one_epoch
+
+    torch.manual_seed(0)
+    H = W = 20
+    n = 6
+    cfg = pipeline_cfg(H, W, 200, 32, 0.0, chunk=131072)
+    cfg.ray_sampler.n_pts_per_ray_training = 32
+    cfg.ray_sampler.n_pts_per_ray_evaluation = 32
+    pipe = PIPELINES.build(cfg).to(DEV)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    img = torch.where(((xx - 10) ** 2 + (yy - 10) ** 2 < 36)[..., None], torch.tensor([0.8, 0.7, 0.1]), torch.tensor([0.2, 0.2, 0.6]))
+    feed = DeviceSceneFeed(syn.synth_camera(1, seed=0, jitter=0.0).expand(n, -1, -1), 25.0, img[None].expand(n, -1, -1, -1),
+                           DEV, shuffle=True, seed=1)
+    trainer = FusedTrainer(pipe, lr=5e-4, use_cuda_graph=True)
+    conf = dict(lr=1e-3, min_lr=1e-4, num_iters=120)
+    first = train_one_epoch(trainer, feed, conf, epoch=0, iters_per_epoch=len(feed))
+    for epoch in range(1, 20):
+        feed.set_epoch(epoch)
+        last = train_one_epoch(trainer, feed, conf, epoch=epoch, iters_per_epoch=len(feed))
+    trainer.finish()
+    stats = eval_one_epoch(pipe, [feed.batch(0), feed.batch(1)], dataset_len=2)
+    print("epoch stats", first["objective"], "->", last["objective"], "eval psnr", stats["loss_rgb_psnr"])
+    assert trainer.step_count == 120 and last["objective"] < 0.25 * first["objective"]
+    assert stats["loss_rgb_psnr"] > 18.0 and "loss_prev_stage_rgb_mse" in stats

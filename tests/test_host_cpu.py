@@ -255,3 +255,36 @@ def test_fused_trainer_reads_and_writes_reference_checkpoints():
     bad = {"model": ckpt["model"], "optimizer": {"state": {}, "param_groups": [{"params": [0, 1]}]}}
     with pytest.raises(ValueError, match="optimizer state for 2 parameters"):
         trainer.load_state_dict(bad)
+
+
+def test_device_scene_feed_matches_distributed_sampler():
+    """the device-resident feed shards and orders images exactly like the reference's
+    DistributedSampler (runners/utils.py:112-116) and yields per-image views with the dataset wrappers' field names."""
+    from torch.utils.data import DistributedSampler
+
+    from yanerf.runners import DeviceSceneFeed
+
+    n, H, W = 11, 4, 6
+    poses = torch.randn(n, 3, 4)
+    images = torch.rand(n, H, W, 3)
+    for world in (1, 2, 4):
+        for shuffle in (False, True):
+            for epoch in (0, 3):
+                seen = []
+                for rank in range(world):
+                    feed = DeviceSceneFeed(poses, 1111.0, images, "cpu", rank=rank, world_size=world, shuffle=shuffle, seed=5)
+                    feed.set_epoch(epoch)
+                    ref = DistributedSampler(range(n), num_replicas=world, rank=rank, shuffle=shuffle, seed=5)
+                    ref.set_epoch(epoch)
+                    assert feed.indices() == list(ref) and len(feed) == len(ref)
+                    seen += feed.indices()
+                assert set(seen) == set(range(n))
+    feed = DeviceSceneFeed(poses, torch.full((n,), 2.0), images, "cpu", min_depth=torch.arange(n).float(), shuffle=False)
+    batches = list(feed)
+    assert len(batches) == n and sorted(batches[0]) == ["focal_lengths", "image_rgb", "min_depth", "poses"]
+    b = batches[4]
+    assert b["poses"].shape == (1, 3, 4) and b["focal_lengths"].shape == (1, 1) and b["image_rgb"].shape == (1, H, W, 3)
+    assert torch.equal(b["image_rgb"][0], images[4]) and float(b["min_depth"]) == 4.0
+    assert b["image_rgb"].data_ptr() == feed.image_rgb[4].data_ptr()  # a view, not a copy
+    with pytest.raises(ValueError, match="image_rgb must be"):
+        DeviceSceneFeed(poses, 1.0, images.permute(0, 3, 1, 2), "cpu")
