@@ -51,38 +51,29 @@ __device__ __forceinline__ void bwd_st_shared_v4(uint32_t addr, uint32_t a, uint
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// packed 16-bit pair `dy` zeroed where the forward activation pair `act` is zero (ReLU mask)
-template <int kFmt>
-__device__ __forceinline__ uint32_t mask_pair(uint32_t dy, uint32_t act) {
-  if (kFmt == 1) {
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&act);
-    const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
-    const __nv_bfloat162 m = __hne2(a, z);  // 1.0 / 0.0 per lane
-    const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&dy), m);
-    return *reinterpret_cast<const uint32_t*>(&r);
-  } else {
-    const __half2 a = *reinterpret_cast<const __half2*>(&act);
-    const __half2 m = __hne2(a, __float2half2_rn(0.f));
-    const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&dy), m);
-    return *reinterpret_cast<const uint32_t*>(&r);
-  }
+// ReLU masks come from the forward kernel's sign stash: bit (31 - j) of word q = "pre-activation of column 32 q + j was
+// negative" (mlp_common.cuh).  Four columns at a time: the 4 bits are spread to the most significant bits of the 4 bytes
+// of a word by one multiplication (bit i lands at 7 (i + 1) + i, no two products collide), and `prmt` in its
+// sign-replicate mode turns a byte's top bit into a 0xFFFF / 0x0000 half-word mask.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// `p0` holds columns (j, j+1), `p1` columns (j+2, j+3) as packed 16-bit pairs, j a multiple of 4 inside mask word `w`
+__device__ __forceinline__ void mask_quad(uint32_t w, int j, uint32_t& p0, uint32_t& p1) {
+  const uint32_t t = (w >> (28 - j)) & 0xFu;        // bit 3 = column j ... bit 0 = column j + 3
+  const uint32_t s = t * 0x10204080u;               // byte 3 msb = column j, byte 2 = j + 1, byte 1 = j + 2, byte 0 = j + 3
+  p0 &= ~prmt(s, 0u, 0xAABBu);                      // low half <- sign(byte 3), high half <- sign(byte 2)
+  p1 &= ~prmt(s, 0u, 0x8899u);                      // low half <- sign(byte 1), high half <- sign(byte 0)
 }
 
 // epilogue of one 128-column half of a data-gradient step.
 // kMode 0: dY = acc; 1: dY = mask(acc); 2: dY = mask(acc + d_density * w_density)
 template <int kFmt, int kMode>
-__device__ __forceinline__ void dgrad_epilogue_half(uint32_t t_addr, int c_lo, const uint8_t* __restrict__ mask_row,
-                                                    uint32_t swz, float dd, const float* __restrict__ wd,
-                                                    uint32_t g_row) {
-  // prefetched mask units of this half (forward activations, 16 bit): 16 x 16 B
-  uint4 m[16];
-  if (kMode != 0) {
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int c = c_lo + u * 8;
-      m[u] = __ldg(reinterpret_cast<const uint4*>(mask_row + (size_t)(c >> 6) * kBlkBytes + ((((c >> 3) & 7) ^ swz) << 4)));
-    }
-  }
+__device__ __forceinline__ void dgrad_epilogue_half(uint32_t t_addr, int c_lo, const uint4 mask, uint32_t swz, float dd,
+                                                    const float* __restrict__ wd, uint32_t g_row) {
+  const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
 #pragma unroll
   for (int cb = 0; cb < 4; ++cb) {
     uint32_t v[32];
@@ -91,23 +82,16 @@ __device__ __forceinline__ void dgrad_epilogue_half(uint32_t t_addr, int c_lo, c
     const int c0 = c_lo + cb * 32;
     uint32_t pk[16];
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < 32; j += 4) {
       float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+      float x2 = __uint_as_float(v[j + 2]), x3 = __uint_as_float(v[j + 3]);
       if (kMode == 2) {
-        x0 = fmaf(dd, __ldg(wd + c0 + j), x0);
-        x1 = fmaf(dd, __ldg(wd + c0 + j + 1), x1);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
+        x0 = fmaf(dd, w.x, x0); x1 = fmaf(dd, w.y, x1); x2 = fmaf(dd, w.z, x2); x3 = fmaf(dd, w.w, x3);
       }
       pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
-    }
-    if (kMode != 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 mu = m[cb * 4 + i];
-        pk[4 * i] = mask_pair<kFmt>(pk[4 * i], mu.x);
-        pk[4 * i + 1] = mask_pair<kFmt>(pk[4 * i + 1], mu.y);
-        pk[4 * i + 2] = mask_pair<kFmt>(pk[4 * i + 2], mu.z);
-        pk[4 * i + 3] = mask_pair<kFmt>(pk[4 * i + 3], mu.w);
-      }
+      pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
+      if (kMode != 0) mask_quad(mw[cb], j, pk[j / 2], pk[j / 2 + 1]);
     }
     const uint32_t blk = g_row + (c0 >> 6) * kBlkBytes;
     const uint32_t u0 = ((c0 >> 5) & 1) * 4;
@@ -241,7 +225,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       const bool valid = gidx < p.n_points;
       // rows of partner tiles beyond the end alias tile 0 of the stash for reads; their gradients are zero
       const int64_t rtile = tile_live ? tile : 0;
-      const uint8_t* stash_row = p.stash + (size_t)rtile * blocks_per_tile * kBlkBytes + (size_t)row * 128;
+      // this row's ReLU sign masks (32 B per layer): mask m at A.mask_offset(m)
+      const uint8_t* mask_rows = p.stash + (size_t)rtile * blocks_per_tile * kBlkBytes + (size_t)row * 32;
       uint8_t* gstash_tile = p.gstash + (size_t)rtile * blocks_per_tile * kBlkBytes;
 
       if (leader) bulk_wait_read<0>();
@@ -257,11 +242,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         }
       }
       {
-        const uint8_t* hid_row = stash_row + (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
+        const uint4 hm = __ldg(reinterpret_cast<const uint4*>(mask_rows + A.mask_offset(n)));  // colour hidden layer
 #pragma unroll 1
         for (int u = 0; u < 16; ++u) {  // 16 units of 8 columns = 128 hidden features
           const int c0 = u * 8;
-          const uint4 hu = __ldg(reinterpret_cast<const uint4*>(hid_row + (size_t)(c0 >> 6) * kBlkBytes + ((((c0 >> 3) & 7) ^ swz) << 4)));
+          const int q = u >> 2;
+          const uint32_t mw = q == 0 ? hm.x : (q == 1 ? hm.y : (q == 2 ? hm.z : hm.w));
           float x[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = 0.f;
@@ -273,10 +259,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
             x[4] = fmaf(ds[c], wb.x, x[4]); x[5] = fmaf(ds[c], wb.y, x[5]);
             x[6] = fmaf(ds[c], wb.z, x[6]); x[7] = fmaf(ds[c], wb.w, x[7]);
           }
-          const uint32_t p0 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[0], x[1]), hu.x);
-          const uint32_t p1 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[2], x[3]), hu.y);
-          const uint32_t p2 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[4], x[5]), hu.z);
-          const uint32_t p3 = mask_pair<kFmt>(Half2Pack<kFmt>::pack(x[6], x[7]), hu.w);
+          uint32_t p0 = Half2Pack<kFmt>::pack(x[0], x[1]), p1 = Half2Pack<kFmt>::pack(x[2], x[3]);
+          uint32_t p2 = Half2Pack<kFmt>::pack(x[4], x[5]), p3 = Half2Pack<kFmt>::pack(x[6], x[7]);
+          mask_quad(mw, c0 & 31, p0, p1);
+          mask_quad(mw, (c0 & 31) + 4, p2, p3);
           bwd_st_shared_v4(g_row + (c0 >> 6) * kBlkBytes + ((((c0 >> 3) & 7) ^ swz) << 4), p0, p1, p2, p3);
         }
       }
@@ -296,7 +282,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         const int l = n + 1 - st;                 // layer whose data gradient was just multiplied
         const int prev = l - 1;                   // mma layer whose output gradient this epilogue produces
         const bool last = st == n_steps - 1;
-        const uint8_t* mask_row = stash_row + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
+        // sign masks of both halves, requested before the wait for the accumulator (step 0 feeds the intermediate
+        // layer, which has no activation)
+        uint4 mk0 = make_uint4(0u, 0u, 0u, 0u), mk1 = mk0;
+        if (st != 0) {
+          const uint4* mp = reinterpret_cast<const uint4*>(mask_rows + A.mask_offset(prev));
+          mk0 = __ldg(mp);
+          mk1 = __ldg(mp + 1);
+        }
         // ---- half 0
         mbar_wait(my_hfull, hf_phase0);
         hf_phase0 ^= 1;
@@ -305,9 +298,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         tc_fence_after();
         if (leader) bulk_wait_read<0>();
         bwd_named_bar_sync(1 + g, 128);
-        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mask_row, swz, dd, wd, g_row);
-        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mask_row, swz, dd, wd, g_row);
-        else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mask_row, swz, dd, wd, g_row);
+        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mk0, swz, dd, wd, g_row);
+        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
+        else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mk0, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
         if (!last) mbar_arrive(my_epi);
@@ -315,9 +308,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         mbar_wait(my_hfull + 8, hf_phase1);
         hf_phase1 ^= 1;
         tc_fence_after();
-        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mask_row, swz, dd, wd, g_row);
-        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mask_row, swz, dd, wd, g_row);
-        else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mask_row, swz, dd, wd, g_row);
+        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mk1, swz, dd, wd, g_row);
+        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
+        else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mk1, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
         if (!last) mbar_arrive(my_epi + 8);

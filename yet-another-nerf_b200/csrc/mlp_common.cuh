@@ -15,6 +15,7 @@ constexpr int kMaxLayers = 12;
 constexpr int kDirPad = 128;       // padded width of the colour hidden layer
 constexpr int kBiasBlkBytes = 4096;  // [128 x 16] 16-bit, no swizzle (8x8 core matrices)
 constexpr int kHeadBlkBytes = 4096;  // colour head [16 x 128] 16-bit: two swizzled [16 x 64] sub-blocks
+constexpr int kMaskBytes = 4096;     // sign mask of one layer and tile: 128 rows x 256 bits
 constexpr int kHeadN = 16;           // UMMA N of the colour head (color_dim <= 3 rows used)
 
 struct Arch {
@@ -104,9 +105,15 @@ struct Arch {
   }
   __host__ __device__ int total_stages_all() const { return bwd_stage_offset(0) + bwd_stages(0); }
 
-  // stash per tile: embedding block, then the 16-bit output image of every mma layer (4 blocks; 2 for colour hidden)
-  __host__ __device__ int stash_blocks_per_tile() const { return 1 + 4 * (n_layers + 1) + 2; }
+  // stash per tile: embedding block, then the 16-bit output image of every mma layer (4 blocks; 2 for colour hidden),
+  // then the ReLU sign masks: one bit per activation, [mask][128 rows][8 words] = 4 KB per ReLU layer (mask m = trunk
+  // layer m for m < n_layers, m = n_layers for the colour hidden layer); bit (31 - j) of word q = "pre-activation of
+  // column 32 q + j is negative".  The data-gradient kernel reads these 36 KB per tile instead of 608 KB of activations.
+  __host__ __device__ int act_blocks_per_tile() const { return 1 + 4 * (n_layers + 1) + 2; }
+  __host__ __device__ int mask_blocks_per_tile() const { return ((n_layers + 1) * kMaskBytes + kBlkBytes - 1) / kBlkBytes; }
+  __host__ __device__ int stash_blocks_per_tile() const { return act_blocks_per_tile() + mask_blocks_per_tile(); }
   __host__ __device__ int stash_block_of_layer(int l) const { return 1 + 4 * l; }
+  __host__ __device__ size_t mask_offset(int m) const { return (size_t)act_blocks_per_tile() * kBlkBytes + (size_t)m * kMaskBytes; }
 };
 
 inline Arch arch_from_c(const yn_mlp_arch* a) {

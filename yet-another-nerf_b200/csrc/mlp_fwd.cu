@@ -114,11 +114,20 @@ __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
 
+// shifts the sign bit of x into the mask word (most significant bit first): after 32 calls bit (31 - j) is the sign of
+// the j-th value
+__device__ __forceinline__ uint32_t push_sign(uint32_t word, float x) {
+  return __funnelshift_l(__float_as_uint(x), word, 1);
+}
+__device__ __forceinline__ void store_mask_half(uint8_t* mask_row, int half, const uint32_t (&w)[4]) {
+  *reinterpret_cast<uint4*>(mask_row + half * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // last trunk layer: processes accumulator columns [c_lo, c_lo + 128) of one row: ReLU -> 16-bit -> activation blocks
 // (c_lo / 64, c_lo / 64 + 1), and the fp32 density head on the un-rounded activations
 template <int kFmt>
 __device__ __forceinline__ void epilogue_half_density(uint32_t t_addr, int c_lo, const float* __restrict__ wd,
-                                                      float& dens, uint32_t act_row, uint32_t swz) {
+                                                      float& dens, uint32_t act_row, uint32_t swz, uint8_t* mask_row) {
 #pragma unroll 1
   for (int cb = 0; cb < 4; cb += 2) {
     uint32_t v[2][32];
@@ -129,11 +138,15 @@ __device__ __forceinline__ void epilogue_half_density(uint32_t t_addr, int c_lo,
     for (int h = 0; h < 2; ++h) {
       const int c0 = c_lo + (cb + h) * 32;
       uint32_t pk[16];
+      uint32_t sign = 0u;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         // the bias is already in the accumulator (folded into the MMA)
         const float x0 = fmaxf(__uint_as_float(v[h][j]), 0.f), x1 = fmaxf(__uint_as_float(v[h][j + 1]), 0.f);
         const float x2 = fmaxf(__uint_as_float(v[h][j + 2]), 0.f), x3 = fmaxf(__uint_as_float(v[h][j + 3]), 0.f);
+        if (mask_row)
+          sign = push_sign(push_sign(push_sign(push_sign(sign, __uint_as_float(v[h][j])), __uint_as_float(v[h][j + 1])),
+                                     __uint_as_float(v[h][j + 2])), __uint_as_float(v[h][j + 3]));
         const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
         dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
         dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
@@ -145,6 +158,7 @@ __device__ __forceinline__ void epilogue_half_density(uint32_t t_addr, int c_lo,
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      if (mask_row) *reinterpret_cast<uint32_t*>(mask_row + (c0 >> 5) * 4) = sign;
     }
   }
 }
@@ -155,19 +169,22 @@ __device__ __forceinline__ void epilogue_half_density(uint32_t t_addr, int c_lo,
 // the MMAs that are still running.
 template <int kFmt, bool kRelu, typename BeforeStore>
 __device__ __forceinline__ void epilogue_half_plain(uint32_t t_addr, int c_lo, uint32_t act_row, uint32_t swz,
-                                                    BeforeStore&& before_store) {
+                                                    uint8_t* mask_row, BeforeStore&& before_store) {
   uint32_t v[4][32];
 #pragma unroll
   for (int q = 0; q < 4; ++q) tmem_ld32(t_addr + c_lo + q * 32, v[q]);
   tmem_ld_wait();
   uint32_t pk[64];
+  uint32_t sign[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
       const float x0 = __uint_as_float(v[q][j]), x1 = __uint_as_float(v[q][j + 1]);
       pk[q * 16 + j / 2] = kRelu ? pack_relu<kFmt>(x0, x1) : Half2Pack<kFmt>::pack(x0, x1);
+      if (kRelu && mask_row) sign[q] = push_sign(push_sign(sign[q], x0), x1);
     }
+  if (kRelu && mask_row) store_mask_half(mask_row, c_lo >> 7, sign);
   before_store();
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -185,7 +202,7 @@ __device__ __forceinline__ void epilogue_half_plain(uint32_t t_addr, int c_lo, u
 // activation blocks 0,1 = the A operand of the colour-head MMA
 template <int kFmt>
 __device__ __forceinline__ void epilogue_color_hidden(uint32_t t_addr, const float* __restrict__ dirbias_row,
-                                                      uint32_t act_row, uint32_t swz) {
+                                                      uint32_t act_row, uint32_t swz, uint8_t* mask_row) {
 #pragma unroll 1
   for (int cb = 0; cb < 2; ++cb) {  // one 64-column activation block per iteration
     uint32_t v[2][32];
@@ -196,15 +213,20 @@ __device__ __forceinline__ void epilogue_color_hidden(uint32_t t_addr, const flo
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t pk[16];
+      uint32_t sign = 0u;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(dirbias_row + cb * 64 + h * 32 + j));
-        pk[j / 2] = pack_relu<kFmt>(__uint_as_float(v[h][j]) + b.x, __uint_as_float(v[h][j + 1]) + b.y);
-        pk[j / 2 + 1] = pack_relu<kFmt>(__uint_as_float(v[h][j + 2]) + b.z, __uint_as_float(v[h][j + 3]) + b.w);
+        const float x0 = __uint_as_float(v[h][j]) + b.x, x1 = __uint_as_float(v[h][j + 1]) + b.y;
+        const float x2 = __uint_as_float(v[h][j + 2]) + b.z, x3 = __uint_as_float(v[h][j + 3]) + b.w;
+        pk[j / 2] = pack_relu<kFmt>(x0, x1);
+        pk[j / 2 + 1] = pack_relu<kFmt>(x2, x3);
+        if (mask_row) sign = push_sign(push_sign(push_sign(push_sign(sign, x0), x1), x2), x3);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         st_shared_v4(blk + (((h * 4 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+      if (mask_row) *reinterpret_cast<uint32_t*>(mask_row + (cb * 2 + h) * 4) = sign;
     }
   }
 }
@@ -527,17 +549,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           }
         };
         const bool plain = !is_color && !is_last_trunk;
+        // ReLU sign mask of this layer and row (training only): trunk layer l -> mask l, colour hidden -> mask n_layers
+        uint8_t* mask_row = nullptr;
+        if (kStash && tile_live && !is_inter)
+          mask_row = stash_tile + A.mask_offset(is_color ? A.n_layers : l) + (size_t)row * 32;
         if (p.debug & 1) {
           before_store0();
         } else if (plain) {
-          if (is_inter) epilogue_half_plain<kFmt, false>(t_row, 0, act_row, swz, before_store0);
-          else epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, before_store0);
+          if (is_inter) epilogue_half_plain<kFmt, false>(t_row, 0, act_row, swz, nullptr, before_store0);
+          else epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, mask_row, before_store0);
         } else if (is_color) {
           before_store0();
-          epilogue_color_hidden<kFmt>(t_row, bias, act_row, swz);
+          epilogue_color_hidden<kFmt>(t_row, bias, act_row, swz, mask_row);
         } else {
           before_store0();
-          epilogue_half_density<kFmt>(t_row, 0, wd, dens, act_row, swz);
+          epilogue_half_density<kFmt>(t_row, 0, wd, dens, act_row, swz, mask_row);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -551,11 +577,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tr.log(l << 8 | 4);
           if (p.debug & 1) {
           } else if (is_inter)
-            epilogue_half_plain<kFmt, false>(t_row, 128, act_row, swz, [] {});
+            epilogue_half_plain<kFmt, false>(t_row, 128, act_row, swz, nullptr, [] {});
           else if (!is_last_trunk)
-            epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, [] {});
+            epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, mask_row, [] {});
           else
-            epilogue_half_density<kFmt>(t_row, 128, wd, dens, act_row, swz);
+            epilogue_half_density<kFmt>(t_row, 128, wd, dens, act_row, swz, mask_row);
           tc_fence_before();
           fence_proxy_async_smem();
         }
