@@ -14,6 +14,7 @@
 //   3. small SIMT kernels     the N=1 / N=3 heads and the per-ray direction part of LinearWithRepeat
 //                             (models/utils.py:207-211).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "mlp_common.cuh"
 #include "sm100_ptx.cuh"
@@ -688,11 +689,13 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
       cudaFuncSetAttribute(dgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
     if (first_use(reinterpret_cast<const void*>(wgrad)))
       cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
-    dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
-    wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
-    heads<<<(int)(n_tiles < 4 * sms ? n_tiles : 4 * sms), 256, 0, stream>>>(p);
+    // YN_BWD_DEBUG (timing experiments only, wrong gradients; tools/bwd_split.sh): bit mask of kernels to skip
+    static const int skip = getenv("YN_BWD_DEBUG") ? atoi(getenv("YN_BWD_DEBUG")) : 0;
+    if (!(skip & 1)) dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
+    if (!(skip & 2)) wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
+    if (!(skip & 4)) heads<<<(int)(n_tiles < 4 * sms ? n_tiles : 4 * sms), 256, 0, stream>>>(p);
     const int64_t ray_blocks = (p.R + 7) / 8;
-    dir<<<(int)(ray_blocks < 2 * sms ? ray_blocks : 2 * sms), 256, 0, stream>>>(p);
+    if (!(skip & 8)) dir<<<(int)(ray_blocks < 2 * sms ? ray_blocks : 2 * sms), 256, 0, stream>>>(p);
   };
   if (A.fmt == 1)
     run(mlp_bwd_dgrad_kernel<1>, mlp_bwd_wgrad_kernel<1>, mlp_bwd_heads_kernel<1>, mlp_bwd_dir_kernel<1>);
