@@ -55,7 +55,15 @@ if only in ("", "composite"):
     sig.requires_grad_(True); rgb.requires_grad_(True)
     f, dep, op, w = ops.composite(sig, rgb, z, d, cfg)
     ms = timeit(lambda: torch.autograd.grad(f, (sig, rgb), gf, retain_graph=True))
-    report("composite_bwd P=192", 40 * P + 32, ms)
+    report("composite_bwd P=192 (torch.autograd.grad call: kernel + output allocation + autograd glue)", 40 * P + 32, ms)
+    ops.Profiler.reset()
+    ops.Profiler.enabled = True
+    for _ in range(10):
+        torch.autograd.grad(f, (sig, rgb), gf, retain_graph=True)
+    torch.cuda.synchronize()
+    ops.Profiler.enabled = False
+    calls, total = ops.Profiler.summary()["yn_composite_bwd"]
+    report("composite_bwd P=192 (kernel only, CUDA events around yn_composite_bwd)", 40 * P + 32, total / calls)
     del sig, rgb, z, d, f, dep, op, w
 if only in ("", "pdf"):
     for P, n in ((64, 128), (192, 128)):

@@ -22,7 +22,7 @@ class Profiler:
     enabled = False
     records: list = []
     launches = 0
-    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 2}
+    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 2, "yn_mlp_bwd": 4}  # dgrad, wgrad, heads, direction
 
     @classmethod
     def reset(cls):
