@@ -40,6 +40,7 @@ struct BwdParams {
   const uint8_t* stash;
   uint8_t* gstash;
   float* grads;
+  float* tbuf;  // [128][256] fp32: T = dY_colour^T relu(h_last) (see mlp_bwd_inter_kernel); then [128] column sums of dY_colour
   int64_t n_points;
   int64_t R;
   int P;
@@ -316,7 +317,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         fence_proxy_async_smem();
         if (!last) mbar_arrive(my_epi + 8);
         bwd_named_bar_sync(1 + g, 128);
-        if (leader && tile_live) {
+        // (step 0 produces the gradient of the intermediate layer's output: only the next step reads it, see
+        // mlp_bwd_inter_kernel for why no weight-gradient job needs it)
+        if (leader && tile_live && st != 0) {
           uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
           for (int b = 0; b < 4; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, g_g + b * kBlkBytes, kBlkBytes);
           bulk_commit();
@@ -358,16 +361,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
   const int n = A.n_layers;
   const int job = blockIdx.x % n_jobs;
   const int split = blockIdx.x / n_jobs;
-  // job -> (layer, output half); the colour hidden layer has a single half
-  const int l = job < 2 * (n + 1) ? job / 2 : n + 1;
-  const int mh = job < 2 * (n + 1) ? job % 2 : 0;
+  // job -> (layer, output half) for the n trunk layers, then the colour hidden layer (a single half).  The intermediate
+  // layer has no job: its gradient comes out of the colour job's product (mlp_bwd_inter_kernel).
+  const int l = job < 2 * n ? job / 2 : n + 1;
+  const int mh = job < 2 * n ? job % 2 : 0;
+  const bool color_job = l == n + 1;
   const bool has_hidden = l >= 1;
   const bool has_emb = A.has_emb(l);
   const bool use_ones = !has_emb;  // bias gradient via a tile of ones when there is no constant-1 channel
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int blocks_per_tile = A.stash_blocks_per_tile();
-  // X_l: output of the previous mma layer (the colour hidden layer reads the intermediate output)
-  const int xprev = l - 1;
+  // X_l: output of the previous mma layer; the colour job multiplies against the LAST TRUNK layer's output instead of the
+  // intermediate output (which is not stashed): T = dY_c^T relu(h_last)
+  const int xprev = color_job ? n - 1 : l - 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
     mbar_wait(bar_done, 0);
     tc_fence_after();
     const int dout = A.dout(l), din = A.din(l), hin = A.hidden_in(l), exyz = A.embed_xyz();
-    float* W = p.grads + A.w_offset(l) + (int64_t)out * din;
+    float* W = color_job ? p.tbuf + (int64_t)out * kInner : p.grads + A.w_offset(l) + (int64_t)out * din;
     float* bgrad = p.grads + A.b_offset(l) + out;
     const bool row_ok = out < dout;
     if (has_hidden) {
@@ -477,7 +483,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
       uint32_t v[32];
       tmem_ld32(t_row + 320, v);  // columns 320..335 hold 16 identical sums (the rest is unused)
       tmem_ld_wait();
-      if (row_ok) atomicAdd(bgrad, __uint_as_float(v[0]));
+      if (row_ok) {
+        atomicAdd(bgrad, __uint_as_float(v[0]));
+        if (color_job) atomicAdd(p.tbuf + kDirPad * kInner + out, __uint_as_float(v[0]));
+      }
     }
   }
   tc_fence_before();
@@ -672,6 +681,54 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
   }
 }
 
+// The intermediate layer is linear (no activation) and feeds only the colour hidden layer:
+//   inter = relu(h) W_i^T + b_i,   d_inter = dY_c W_c[:, :H]        (h = last trunk output, H = hidden_last)
+// so with T = dY_c^T relu(h)  [hidden_dir x H]  and  s = sum_points dY_c  [hidden_dir]  (both accumulated by the colour
+// weight-gradient job over the trunk output the intermediate layer's own job would have read):
+//   dW_c[:, :H] = dY_c^T inter = T W_i^T + s b_i^T,    dW_i = d_inter^T relu(h) = W_c[:, :H]^T T,    db_i = W_c[:, :H]^T s.
+// Neither the intermediate output nor its gradient has to be written to HBM (16 blocks of 16 KB per tile less traffic),
+// and the two products no longer see a 16-bit rounding of inter / d_inter.  fp32 master weights, two 128x256x256
+// contractions: microseconds.  Block b < H: row b of dW_i and db_i[b]; block H + j: row j of dW_c[:, :H].
+__global__ void __launch_bounds__(256) mlp_bwd_inter_kernel(const BwdParams p) {
+  const Arch& A = p.arch;
+  const int n = A.n_layers, H = A.hidden_last, D = A.hidden_dir;
+  const int dinc = A.din(n + 1);
+  const float* Wi = p.params + A.w_offset(n);
+  const float* bi = p.params + A.b_offset(n);
+  const float* Wc = p.params + A.w_offset(n + 1);
+  const float* T = p.tbuf;
+  const float* svec = p.tbuf + kDirPad * kInner;
+  __shared__ float s_row[kInner];
+  const int t = threadIdx.x;
+  if ((int)blockIdx.x < H) {
+    const int o = blockIdx.x;
+    if (t < D) s_row[t] = Wc[(int64_t)t * dinc + o];  // column o of W_c
+    __syncthreads();
+    if (t < H) {
+      float acc = 0.f;
+      for (int j = 0; j < D; ++j) acc = fmaf(s_row[j], T[j * kInner + t], acc);
+      p.grads[A.w_offset(n) + (int64_t)o * H + t] += acc;
+    }
+    if (t == 0) {
+      float acc = 0.f;
+      for (int j = 0; j < D; ++j) acc = fmaf(s_row[j], svec[j], acc);
+      p.grads[A.b_offset(n) + o] += acc;
+    }
+  } else {
+    const int j = blockIdx.x - H;
+    if (t < H) s_row[t] = T[j * kInner + t];
+    __syncthreads();
+    if (t < H) {  // t = output feature o of the intermediate layer
+      float acc = svec[j] * bi[t];
+      const float* w = Wi + (int64_t)t * H;
+      for (int k = 0; k < H; ++k) acc = fmaf(s_row[k], w[k], acc);
+      p.grads[A.w_offset(n + 1) + (int64_t)j * dinc + t] += acc;
+    }
+  }
+}
+
+constexpr size_t kTbufBytes = (size_t)(kDirPad * kInner + kDirPad) * sizeof(float);
+
 static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
   const Arch& A = p.arch;
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
@@ -680,7 +737,7 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = (int)(n_pairs < sms ? n_pairs : sms);
-  const int n_jobs = 2 * (A.n_layers + 1) + 1;
+  const int n_jobs = 2 * A.n_layers + 1;
   int n_splits = sms / n_jobs;
   if (n_splits < 1) n_splits = 1;
   if (n_splits > n_tiles) n_splits = (int)n_tiles;
@@ -691,8 +748,12 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
       cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
     // YN_BWD_DEBUG (timing experiments only, wrong gradients; tools/bwd_split.sh): bit mask of kernels to skip
     static const int skip = getenv("YN_BWD_DEBUG") ? atoi(getenv("YN_BWD_DEBUG")) : 0;
+    cudaMemsetAsync(p.tbuf, 0, kTbufBytes, stream);
     if (!(skip & 1)) dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
-    if (!(skip & 2)) wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
+    if (!(skip & 2)) {
+      wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
+      mlp_bwd_inter_kernel<<<A.hidden_last + A.hidden_dir, 256, 0, stream>>>(p);
+    }
     if (!(skip & 4)) heads<<<(int)(n_tiles < 4 * sms ? n_tiles : 4 * sms), 256, 0, stream>>>(p);
     const int64_t ray_blocks = (p.R + 7) / 8;
     if (!(skip & 8)) dir<<<(int)(ray_blocks < 2 * sms ? ray_blocks : 2 * sms), 256, 0, stream>>>(p);
@@ -707,8 +768,10 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
 }  // namespace ynb
 
 extern "C" int64_t yn_mlp_bwd_workspace_bytes(const yn_mlp_arch* arch, int64_t n_points) {
-  // the gradient stash mirrors the activation stash (one 16-bit dY image per layer and tile)
-  return yn_mlp_stash_bytes(arch, n_points);
+  // the gradient stash mirrors the activation stash (one 16-bit dY image per layer and tile); then the fp32 scratch of
+  // mlp_bwd_inter_kernel
+  const int64_t sb = yn_mlp_stash_bytes(arch, n_points);
+  return sb < 0 ? sb : sb + (int64_t)ynb::kTbufBytes;
 }
 
 extern "C" int yn_mlp_bwd(const yn_mlp_arch* arch, const float* directions, const float* rgb, const float* d_density,
@@ -730,6 +793,7 @@ extern "C" int yn_mlp_bwd(const yn_mlp_arch* arch, const float* directions, cons
   p.aux = aux;
   p.stash = static_cast<const uint8_t*>(stash);
   p.gstash = static_cast<uint8_t*>(workspace);
+  p.tbuf = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + yn_mlp_stash_bytes(arch, R * P));
   p.grads = grads;
   p.n_points = R * P;
   p.R = R;

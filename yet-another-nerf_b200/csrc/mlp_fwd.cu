@@ -625,7 +625,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         }
         if (kStash) {
           named_bar_sync(1 + g, 128);
-          if (stash_leader && tile_live) {
+          // (the intermediate layer's output is not stashed: no backward kernel reads it, see mlp_bwd_inter_kernel)
+          if (stash_leader && tile_live && !is_inter) {
             uint8_t* dst = stash_tile + (size_t)A.stash_block_of_layer(l) * kBlkBytes;
             const int nblk = is_color ? 2 : 4;
             for (int b = 0; b < nblk; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, act_g + b * kBlkBytes, kBlkBytes);
