@@ -296,7 +296,9 @@ def mlp_forward_operand_rounded(params, spec, origins, directions, lengths, dt):
     """The oracle's `mlp_forward` (nerf_mlp.py:117-177) with the kernel's documented operand rounding inserted:
     embedding, trunk / intermediate weights+biases and every layer output feeding a tensor-core layer are rounded
     to `dt` -- including the colour hidden activations and W2 of the colour head, which is a tensor-core layer too;
-    the density head, the per-ray direction bias and the colour head's bias stay fp32."""
+    the density head, the per-ray direction bias and the colour head's bias stay fp32.  The intermediate layer is
+    linear and merged into the colour hidden layer: ONE rounded weight matrix W_c[:, :H] W_i and bias W_c[:, :H] b_i, the
+    intermediate output itself is never rounded."""
     import torch.nn.functional as F
 
     r = lambda t: _ste_round(t, dt)
@@ -310,10 +312,11 @@ def mlp_forward_operand_rounded(params, spec, origins, directions, lengths, dt):
         y = r(pre)
     raw_density = F.linear(pre, params["density_layer.weight"], params["density_layer.bias"])[..., 0]
     demb = O.harmonic_embedding(F.normalize(directions, dim=-1), spec.n_harmonic_functions_dir)
-    inter = r(F.linear(y, r(params["intermediate_linear.weight"]), r(params["intermediate_linear.bias"])))
     h = spec.n_hidden_neurons_xyz
     wc = params["color_layer.0.weight"]
-    hid = r(torch.relu(F.linear(inter, r(wc[:, :h]), None) + (F.linear(demb, wc[:, h:], params["color_layer.0.bias"]))[:, None, :]))
+    w_ci = r(wc[:, :h] @ params["intermediate_linear.weight"])
+    b_ci = r(wc[:, :h] @ params["intermediate_linear.bias"])
+    hid = r(torch.relu(F.linear(y, w_ci, b_ci) + (F.linear(demb, wc[:, h:], params["color_layer.0.bias"]))[:, None, :]))
     rgb = torch.sigmoid(F.linear(hid, r(params["color_layer.2.weight"]), params["color_layer.2.bias"]))
     return raw_density, rgb
 

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
   const int lane = threadIdx.x & 31;
   const Arch& A = p.arch;
   const int n = A.n_layers;
-  const int n_steps = n + 1;  // layers n+1 (colour hidden), n (intermediate), n-1 .. 1
+  const int n_steps = n + 1;  // step 0: merged colour hidden + intermediate layer; step 1: unused; steps 2..n: trunk n-1 .. 1
   const int64_t n_tiles = (p.n_points + kTileM - 1) / kTileM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const int blocks_per_tile = A.stash_blocks_per_tile();
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       uint32_t slot = 0, phase = 0, ed_phase0 = 0, ed_phase1 = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int st = 0; st < n_steps; ++st) {
+          if (st == 1) continue;            // the intermediate layer is merged into the colour hidden layer (mlp_common.cuh)
           const int nkb = st == 0 ? 2 : 4;  // reduction over the layer's outputs (128 for the colour hidden layer)
           mbar_wait(my_epi, ed_phase0);
           ed_phase0 ^= 1;
@@ -281,17 +282,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       }
 
       for (int st = 0; st < n_steps; ++st) {
+        if (st == 1) continue;                    // merged intermediate layer: no step of its own
         const int l = n + 1 - st;                 // layer whose data gradient was just multiplied
-        const int prev = l - 1;                   // mma layer whose output gradient this epilogue produces
-        const bool last = st == n_steps - 1;
-        // sign masks of both halves, requested before the wait for the accumulator (step 0 feeds the intermediate
-        // layer, which has no activation)
-        uint4 mk0 = make_uint4(0u, 0u, 0u, 0u), mk1 = mk0;
-        if (st != 0) {
-          const uint4* mp = reinterpret_cast<const uint4*>(mask_rows + A.mask_offset(prev));
-          mk0 = __ldg(mp);
-          mk1 = __ldg(mp + 1);
-        }
+        // mma layer whose output gradient this epilogue produces; the colour step multiplies by W_ci^T = (W_c[:, :H] W_i)^T
+        // and lands directly on the last trunk layer's output
+        const int prev = st == 0 ? n - 1 : l - 1;
+        const bool last = st == (n_steps == 2 ? 0 : n_steps - 1);  // (step 1 does not exist)
+        // sign masks of both halves, requested before the wait for the accumulator
+        const uint4* mp = reinterpret_cast<const uint4*>(mask_rows + A.mask_offset(prev));
+        const uint4 mk0 = __ldg(mp), mk1 = __ldg(mp + 1);
         // ---- half 0
         mbar_wait(my_hfull, hf_phase0);
         hf_phase0 ^= 1;
@@ -300,8 +299,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         tc_fence_after();
         if (leader) bulk_wait_read<0>();
         bwd_named_bar_sync(1 + g, 128);
-        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mk0, swz, dd, wd, g_row);
-        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
+        // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
+        if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mk0, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
@@ -310,16 +309,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         mbar_wait(my_hfull + 8, hf_phase1);
         hf_phase1 ^= 1;
         tc_fence_after();
-        if (st == 0) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mk1, swz, dd, wd, g_row);
-        else if (st == 1) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
+        // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
+        if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mk1, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
         if (!last) mbar_arrive(my_epi + 8);
         bwd_named_bar_sync(1 + g, 128);
-        // (step 0 produces the gradient of the intermediate layer's output: only the next step reads it, see
-        // mlp_bwd_inter_kernel for why no weight-gradient job needs it)
-        if (leader && tile_live && st != 0) {
+        if (leader && tile_live) {
           uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
           for (int b = 0; b < 4; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, g_g + b * kBlkBytes, kBlkBytes);
           bulk_commit();

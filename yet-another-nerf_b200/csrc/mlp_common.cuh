@@ -27,7 +27,12 @@ struct Arch {
 
   __host__ __device__ int embed_xyz() const { return 3 * (2 * n_freq_xyz + 1); }
   __host__ __device__ int embed_dir() const { return 3 * (2 * n_freq_dir + 1); }
-  __host__ __device__ int n_mma_layers() const { return n_layers + 2; }  // trunk + intermediate + colour hidden
+  // mma layer numbering: l < n_layers trunk, l == n_layers the intermediate layer, l == n_layers + 1 the colour hidden
+  // layer.  The intermediate layer is linear and feeds only the colour hidden layer, so the kernels never execute it: the
+  // weight image of the colour hidden layer holds the PRODUCT  W_ci = W_c[:, :H] W_i  (fp32, rounded once) and its bias
+  // stage  b_ci = W_c[:, :H] b_i;  `merged(l)` marks the skipped layer.  Parameters and gradients stay per layer.
+  __host__ __device__ int n_mma_layers() const { return n_layers + 2; }
+  __host__ __device__ bool merged(int l) const { return l == n_layers; }
   __host__ __device__ bool has_emb(int l) const { return l == 0 || (l < n_layers && ((skip_mask >> l) & 1u)); }
   __host__ __device__ int nkb_hidden(int l) const { return l == 0 ? 0 : 4; }
   __host__ __device__ int nkb(int l) const { return nkb_hidden(l) + (has_emb(l) ? 1 : 0); }
@@ -36,9 +41,9 @@ struct Arch {
   // "bias block": a K=16 MMA of the embedding block's last slice (whose channel 63 is the constant 1) with a
   // [128 x 16] weight slice holding the bias in column 15.  Layers WITH an embedding block carry the bias in
   // column 63 of that block.  The colour hidden layer adds its per-ray bias in the epilogue.
-  __host__ __device__ bool has_bias_stage(int l) const { return l <= n_layers && !has_emb(l); }
+  __host__ __device__ bool has_bias_stage(int l) const { return !has_emb(l); }  // (colour hidden: b_ci)
   __host__ __device__ int stages_per_half(int l) const { return nkb(l) + (has_bias_stage(l) ? 1 : 0); }
-  __host__ __device__ int stages(int l) const { return stages_per_half(l) * nnh(l); }
+  __host__ __device__ int stages(int l) const { return merged(l) ? 0 : stages_per_half(l) * nnh(l); }
   __host__ __device__ int stage_offset(int l) const {
     int s = 0;
     for (int i = 0; i < l; ++i) s += stages(i);
@@ -89,13 +94,15 @@ struct Arch {
   __host__ __device__ int aux_bd() const { return aux_wd() + kInner; }
   __host__ __device__ int aux_w2() const { return aux_bd() + 4; }
   __host__ __device__ int aux_b2() const { return aux_w2() + 4 * kDirPad; }
-  __host__ __device__ int aux_floats() const { return aux_b2() + 4; }
+  __host__ __device__ int aux_wci() const { return aux_b2() + 4; }                 // [kDirPad][kInner] fp32: W_c[:, :H] W_i
+  __host__ __device__ int aux_bci() const { return aux_wci() + kDirPad * kInner; }  // [kDirPad]: W_c[:, :H] b_i
+  __host__ __device__ int aux_floats() const { return aux_bci() + kDirPad; }
 
   // weight image: forward stages (W as [n][k] K-major blocks), then for the backward data-gradient the
   // transposed stages (W^T as [k][n] blocks): see mlp_pack.cu
   __host__ __device__ int bwd_stages(int l) const {
     // dgrad of layer l: output columns = hidden_in(l) padded to 256 (none for layer 0), reduction over dout (256 / 128)
-    if (l == 0) return 0;
+    if (l == 0 || merged(l)) return 0;
     return 2 * (l == n_layers + 1 ? 2 : 4);
   }
   __host__ __device__ int bwd_stage_offset(int l) const {

@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         int s = 0;
         for (int l = 0; l < L; ++l) {
+          if (A.merged(l)) continue;  // the intermediate layer lives inside the colour hidden layer's weights
           const int per_half = A.stages_per_half(l), nkb = A.nkb(l);
           for (int j = 0; j < per_half * A.nnh(l); ++j, ++s) {
             const uint32_t bytes = (j % per_half) == nkb ? kBiasBlkBytes : kBlkBytes;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       tr.init(p.trace, g);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int l = 0; l < L; ++l) {
+          if (A.merged(l)) continue;
           const int nkbh = A.nkb_hidden(l);
           const int nkb = A.nkb(l);
           const int nnh = A.nnh(l);
@@ -522,12 +524,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
 
       float dens = 0.f;
       for (int l = 0; l < L; ++l) {
+        if (A.merged(l)) continue;
         const bool is_color = (l == L - 1);
-        const bool is_inter = (l == L - 2);
         const bool is_last_trunk = (l == L - 3);
         const float* bias = is_color ? p.dirbias + ray * kDirPad : p.aux + A.aux_bias(l);
         const float* wd = p.aux + A.aux_wd();
-        if (is_inter) {  // the colour layer's per-ray bias row (512 B): pull it into L1 one layer ahead
+        if (is_last_trunk) {  // the colour layer's per-ray bias row (512 B): pull it into L1 one layer ahead
           const float* row_bias = p.dirbias + ray * kDirPad;
 #pragma unroll
           for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(row_bias + 32 * i));
@@ -551,13 +553,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         const bool plain = !is_color && !is_last_trunk;
         // ReLU sign mask of this layer and row (training only): trunk layer l -> mask l, colour hidden -> mask n_layers
         uint8_t* mask_row = nullptr;
-        if (kStash && tile_live && !is_inter)
+        if (kStash && tile_live)
           mask_row = stash_tile + A.mask_offset(is_color ? A.n_layers : l) + (size_t)row * 32;
         if (p.debug & 1) {
           before_store0();
         } else if (plain) {
-          if (is_inter) epilogue_half_plain<kFmt, false>(t_row, 0, act_row, swz, nullptr, before_store0);
-          else epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, mask_row, before_store0);
+          epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, mask_row, before_store0);
         } else if (is_color) {
           before_store0();
           epilogue_color_hidden<kFmt>(t_row, bias, act_row, swz, mask_row);
@@ -576,9 +577,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tc_fence_after();
           tr.log(l << 8 | 4);
           if (p.debug & 1) {
-          } else if (is_inter)
-            epilogue_half_plain<kFmt, false>(t_row, 128, act_row, swz, nullptr, [] {});
-          else if (!is_last_trunk)
+          } else if (!is_last_trunk)
             epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, mask_row, [] {});
           else
             epilogue_half_density<kFmt>(t_row, 128, wd, dens, act_row, swz, mask_row);
@@ -625,8 +624,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         }
         if (kStash) {
           named_bar_sync(1 + g, 128);
-          // (the intermediate layer's output is not stashed: no backward kernel reads it, see mlp_bwd_inter_kernel)
-          if (stash_leader && tile_live && !is_inter) {
+          if (stash_leader && tile_live) {
             uint8_t* dst = stash_tile + (size_t)A.stash_block_of_layer(l) * kBlkBytes;
             const int nblk = is_color ? 2 : 4;
             for (int b = 0; b < nblk; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, act_g + b * kBlkBytes, kBlkBytes);

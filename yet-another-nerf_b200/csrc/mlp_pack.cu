@@ -12,9 +12,49 @@
 
 namespace ynb {
 
+// W_ci = W_c[:, :H] W_i and b_ci = W_c[:, :H] b_i (fp32) into the aux buffer: the merged intermediate + colour hidden layer
+// (mlp_common.cuh).  Block (jt, os) owns 4 rows of W_c and a quarter of the reduction; thread k owns column k; partial
+// sums are added with atomics (the region is zeroed first).
+__global__ void __launch_bounds__(256) fuse_color_kernel(const Arch A, const float* __restrict__ params, float* __restrict__ aux) {
+  constexpr int kRows = 4, kSplit = 4, kChunk = kInner / kSplit;
+  const int jt = blockIdx.x / kSplit, os = blockIdx.x % kSplit;
+  const int n = A.n_layers, H = A.hidden_last, dinc = A.din(n + 1);
+  const float* Wi = params + A.w_offset(n);
+  const float* bi = params + A.b_offset(n);
+  const float* Wc = params + A.w_offset(n + 1);
+  __shared__ float s_wc[kRows][kChunk];
+  const int t = threadIdx.x;
+  {
+    const int jj = t / kChunk, oo = t % kChunk;  // 256 threads = 4 rows x 64 reduction indices
+    const int j = jt * kRows + jj, o = os * kChunk + oo;
+    s_wc[jj][oo] = (j < A.hidden_dir && o < H) ? Wc[(int64_t)j * dinc + o] : 0.f;
+  }
+  __syncthreads();
+  float acc[kRows] = {0.f, 0.f, 0.f, 0.f};
+  if (t < H) {
+    for (int oo = 0; oo < kChunk; ++oo) {
+      const int o = os * kChunk + oo;
+      if (o >= H) break;
+      const float w = Wi[(int64_t)o * H + t];
+#pragma unroll
+      for (int jj = 0; jj < kRows; ++jj) acc[jj] = fmaf(s_wc[jj][oo], w, acc[jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < kRows; ++jj) atomicAdd(aux + A.aux_wci() + (jt * kRows + jj) * kInner + t, acc[jj]);
+  }
+  if (t < kRows) {
+    float b = 0.f;
+    for (int oo = 0; oo < kChunk; ++oo) {
+      const int o = os * kChunk + oo;
+      if (o < H) b = fmaf(s_wc[t][oo], bi[o], b);
+    }
+    atomicAdd(aux + A.aux_bci() + jt * kRows + t, b);
+  }
+}
+
 template <int kFmt>
-__global__ void pack_weights_kernel(const Arch A, const float* __restrict__ params, uint8_t* __restrict__ wpack,
-                                    int n_units) {
+__global__ void pack_weights_kernel(const Arch A, const float* __restrict__ params, const float* __restrict__ aux,
+                                    uint8_t* __restrict__ wpack, int n_units) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_units) return;
   const int s = idx >> 10;  // 1024 16-byte units per block
@@ -62,7 +102,8 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
       if (unit < 256) {
         const int grp = unit >> 4, kc = (unit >> 3) & 1, rr = unit & 7;
         const int n = nh * 128 + grp * 8 + rr;
-        if (kc == 1 && n < A.dout(l)) out.w = Half2Pack<kFmt>::pack(0.f, params[A.b_offset(l) + n]);
+        if (kc == 1 && n < A.dout(l))
+          out.w = Half2Pack<kFmt>::pack(0.f, l == A.n_layers + 1 ? aux[A.aux_bci() + n] : params[A.b_offset(l) + n]);
       }
       *reinterpret_cast<uint4*>(wpack + (size_t)s * kBlkBytes + (size_t)unit * 16) = out;
       return;
@@ -83,7 +124,7 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
           const int k = kb * 64 + c;
           if (k < A.hidden_in(l)) col = k;
         }
-        if (col >= 0) vals[i] = W[(int64_t)n * din + col];
+        if (col >= 0) vals[i] = l == A.n_layers + 1 ? aux[A.aux_wci() + n * kInner + col] : W[(int64_t)n * din + col];
       }
     }
   } else {
@@ -101,7 +142,7 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int k = kb * 64 + u * 8 + i;
-        if (k < A.dout(l)) vals[i] = W[(int64_t)k * din + n];
+        if (k < A.dout(l)) vals[i] = l == A.n_layers + 1 ? aux[A.aux_wci() + k * kInner + n] : W[(int64_t)k * din + n];
       }
     }
   }
@@ -193,11 +234,13 @@ extern "C" int yn_mlp_pack_weights(const yn_mlp_arch* arch, const float* params,
   const ynb::Arch A = ynb::arch_from_c(arch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_units = A.total_stages_all() * 1024;
+  cudaMemsetAsync(aux + A.aux_wci(), 0, (size_t)(A.aux_floats() - A.aux_wci()) * sizeof(float), st);
+  ynb::fuse_color_kernel<<<(ynb::kDirPad / 4) * 4, 256, 0, st>>>(A, params, aux);
   if (A.fmt == 1)
-    ynb::pack_weights_kernel<1><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, static_cast<uint8_t*>(wpack), n_units);
+    ynb::pack_weights_kernel<1><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, aux, static_cast<uint8_t*>(wpack), n_units);
   else
-    ynb::pack_weights_kernel<0><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, static_cast<uint8_t*>(wpack), n_units);
-  const int na = A.aux_floats();
+    ynb::pack_weights_kernel<0><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, aux, static_cast<uint8_t*>(wpack), n_units);
+  const int na = A.aux_wci();  // the small heads and padded biases; [aux_wci, aux_floats) was written by fuse_color_kernel
   ynb::pack_aux_kernel<<<(na + 255) / 256, 256, 0, st>>>(A, params, aux, na);
   return ynb::check_launch("yn_mlp_pack_weights");
 }

@@ -22,7 +22,7 @@ class Profiler:
     enabled = False
     records: list = []
     launches = 0
-    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 2, "yn_mlp_bwd": 4}  # dgrad, wgrad, heads, direction
+    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 3, "yn_mlp_bwd": 5}  # bwd: dgrad, wgrad, inter, heads, direction
 
     @classmethod
     def reset(cls):

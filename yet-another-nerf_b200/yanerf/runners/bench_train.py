@@ -95,6 +95,9 @@ def run_train_bench(args, rank: int, world: int, dev) -> None:
             roofline={"bound": "tensor", "kernel": "mlp fwd + dgrad + wgrad kernels (coarse + fine)", "achieved": round(achieved, 1),
                       "peak": peaks["tensor"], "peak_source": f"{peaks['source']} bf16_tflops_sustained", "unit": "TFLOP/s",
                       "frac": round(achieved / peaks["tensor"], 4), "traffic": None,
+                      "executed_note": "algorithmic FLOPs of SURVEY 8(d) (3 475 200 per point); the kernels issue 3 213 056: the "
+                                       "linear intermediate layer is folded into the colour hidden layer (forward and data "
+                                       "gradient), its weight gradient comes from a 128x256x256 post-product",
                       "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in prof.items()}},
         )
         B.emit(line)
