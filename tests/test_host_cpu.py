@@ -37,10 +37,16 @@ def test_size_queries_and_validation_without_gpu():
     lib = N.lib()
     lego = N.MlpArch(8, 1 << 5, 10, 4, 256, 128, 3, N.FMT_FP16)
     assert lib.yn_mlp_param_count(ctypes.byref(lego)) == 595844
-    n_stages_fwd = 2 + 4 * 10 + 10 + 2 * 10 + 10 + 4  # incl. one 4 KB bias block per half of hidden-only layers
-    assert lib.yn_mlp_wpack_bytes(ctypes.byref(lego)) >= n_stages_fwd * 16384
-    assert lib.yn_mlp_aux_floats(ctypes.byref(lego)) == 9 * 256 + 256 + 4 + 512 + 4
-    assert lib.yn_mlp_stash_bytes(ctypes.byref(lego), 1000) == 8 * (1 + 36 + 2) * 16384
+    # forward stages: layer 0 (embedding block only) 2, four hidden layers (4 blocks + 4 KB bias block) x 2 halves = 40, the skip
+    # layer (4 + embedding) x 2 = 10, two more hidden layers 20, the intermediate layer 0 (folded into the colour hidden
+    # layer), colour hidden 4 + bias = 5, colour head 1; data-gradient stages: colour 4, seven trunk layers x 8
+    n_stages_fwd, n_stages_bwd = 2 + 40 + 10 + 20 + 0 + 5 + 1, 4 + 7 * 8
+    assert lib.yn_mlp_wpack_bytes(ctypes.byref(lego)) == (n_stages_fwd + n_stages_bwd) * 16384
+    # padded biases, density head, colour head, then W_c[:, :H] W_i and W_c[:, :H] b_i of the folded layer
+    assert lib.yn_mlp_aux_floats(ctypes.byref(lego)) == 9 * 256 + 256 + 4 + 512 + 4 + 128 * 256 + 128
+    # per 128-point tile: embedding block, 9 x 4 + 2 activation blocks, 3 blocks holding the nine 4 KB ReLU sign masks
+    assert lib.yn_mlp_stash_bytes(ctypes.byref(lego), 1000) == 8 * (1 + 36 + 2 + 3) * 16384
+    assert lib.yn_mlp_bwd_workspace_bytes(ctypes.byref(lego), 1000) == 8 * 42 * 16384 + (128 * 256 + 128) * 4
     bad = N.MlpArch(8, 1 << 5, 12, 4, 256, 128, 3, N.FMT_FP16)  # 75-channel embedding
     assert lib.yn_mlp_param_count(ctypes.byref(bad)) == -1
     assert b"embedding" in lib.yn_last_error_string()
