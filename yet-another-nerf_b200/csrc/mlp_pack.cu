@@ -13,42 +13,38 @@
 namespace ynb {
 
 // W_ci = W_c[:, :H] W_i and b_ci = W_c[:, :H] b_i (fp32) into the aux buffer: the merged intermediate + colour hidden layer
-// (mlp_common.cuh).  Block (jt, os) owns 4 rows of W_c and a quarter of the reduction; thread k owns column k; partial
-// sums are added with atomics (the region is zeroed first).
+// (mlp_common.cuh).  Block jt owns 4 rows of W_c (kept in shared memory), thread k owns column k and walks the whole
+// reduction in a fixed order: deterministic (the same weights always give the same image), coalesced reads of W_i.
 __global__ void __launch_bounds__(256) fuse_color_kernel(const Arch A, const float* __restrict__ params, float* __restrict__ aux) {
-  constexpr int kRows = 4, kSplit = 4, kChunk = kInner / kSplit;
-  const int jt = blockIdx.x / kSplit, os = blockIdx.x % kSplit;
+  constexpr int kRows = 4;
+  const int jt = blockIdx.x;
   const int n = A.n_layers, H = A.hidden_last, dinc = A.din(n + 1);
   const float* Wi = params + A.w_offset(n);
   const float* bi = params + A.b_offset(n);
   const float* Wc = params + A.w_offset(n + 1);
-  __shared__ float s_wc[kRows][kChunk];
+  __shared__ float s_wc[kRows][kInner];
   const int t = threadIdx.x;
-  {
-    const int jj = t / kChunk, oo = t % kChunk;  // 256 threads = 4 rows x 64 reduction indices
-    const int j = jt * kRows + jj, o = os * kChunk + oo;
-    s_wc[jj][oo] = (j < A.hidden_dir && o < H) ? Wc[(int64_t)j * dinc + o] : 0.f;
+#pragma unroll
+  for (int jj = 0; jj < kRows; ++jj) {
+    const int j = jt * kRows + jj;
+    s_wc[jj][t] = (j < A.hidden_dir && t < H) ? Wc[(int64_t)j * dinc + t] : 0.f;
   }
   __syncthreads();
   float acc[kRows] = {0.f, 0.f, 0.f, 0.f};
   if (t < H) {
-    for (int oo = 0; oo < kChunk; ++oo) {
-      const int o = os * kChunk + oo;
-      if (o >= H) break;
+#pragma unroll 8
+    for (int o = 0; o < H; ++o) {
       const float w = Wi[(int64_t)o * H + t];
 #pragma unroll
-      for (int jj = 0; jj < kRows; ++jj) acc[jj] = fmaf(s_wc[jj][oo], w, acc[jj]);
+      for (int jj = 0; jj < kRows; ++jj) acc[jj] = fmaf(s_wc[jj][o], w, acc[jj]);
     }
-#pragma unroll
-    for (int jj = 0; jj < kRows; ++jj) atomicAdd(aux + A.aux_wci() + (jt * kRows + jj) * kInner + t, acc[jj]);
   }
+#pragma unroll
+  for (int jj = 0; jj < kRows; ++jj) aux[A.aux_wci() + (jt * kRows + jj) * kInner + t] = acc[jj];
   if (t < kRows) {
     float b = 0.f;
-    for (int oo = 0; oo < kChunk; ++oo) {
-      const int o = os * kChunk + oo;
-      if (o < H) b = fmaf(s_wc[t][oo], bi[o], b);
-    }
-    atomicAdd(aux + A.aux_bci() + jt * kRows + t, b);
+    for (int o = 0; o < H; ++o) b = fmaf(s_wc[t][o], bi[o], b);
+    aux[A.aux_bci() + jt * kRows + t] = b;
   }
 }
 
@@ -234,8 +230,7 @@ extern "C" int yn_mlp_pack_weights(const yn_mlp_arch* arch, const float* params,
   const ynb::Arch A = ynb::arch_from_c(arch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_units = A.total_stages_all() * 1024;
-  cudaMemsetAsync(aux + A.aux_wci(), 0, (size_t)(A.aux_floats() - A.aux_wci()) * sizeof(float), st);
-  ynb::fuse_color_kernel<<<(ynb::kDirPad / 4) * 4, 256, 0, st>>>(A, params, aux);
+  ynb::fuse_color_kernel<<<ynb::kDirPad / 4, 256, 0, st>>>(A, params, aux);
   if (A.fmt == 1)
     ynb::pack_weights_kernel<1><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, aux, static_cast<uint8_t*>(wpack), n_units);
   else
