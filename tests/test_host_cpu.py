@@ -39,8 +39,8 @@ def test_size_queries_and_validation_without_gpu():
     assert lib.yn_mlp_param_count(ctypes.byref(lego)) == 595844
     # forward stages: layer 0 (embedding block only) 2, four hidden layers (4 blocks + 4 KB bias block) x 2 halves = 40, the skip
     # layer (4 + embedding) x 2 = 10, two more hidden layers 20, the intermediate layer 0 (folded into the colour hidden
-    # layer), colour hidden 4 + bias = 5, colour head 1; data-gradient stages: colour 4, seven trunk layers x 8
-    n_stages_fwd, n_stages_bwd = 2 + 40 + 10 + 20 + 0 + 5 + 1, 4 + 7 * 8
+    # layer), colour hidden 4 + bias = 5, density head 1, colour head 1; data-gradient stages: colour 4, seven trunk layers x 8
+    n_stages_fwd, n_stages_bwd = 2 + 40 + 10 + 20 + 0 + 5 + 1 + 1, 4 + 7 * 8
     assert lib.yn_mlp_wpack_bytes(ctypes.byref(lego)) == (n_stages_fwd + n_stages_bwd) * 16384
     # padded biases, density head, colour head, then W_c[:, :H] W_i and W_c[:, :H] b_i of the folded layer
     assert lib.yn_mlp_aux_floats(ctypes.byref(lego)) == 9 * 256 + 256 + 4 + 512 + 4 + 128 * 256 + 128

@@ -15,6 +15,7 @@ constexpr int kMaxLayers = 12;
 constexpr int kDirPad = 128;       // padded width of the colour hidden layer
 constexpr int kBiasBlkBytes = 4096;  // [128 x 16] 16-bit, no swizzle (8x8 core matrices)
 constexpr int kHeadBlkBytes = 4096;  // colour head [16 x 128] 16-bit: two swizzled [16 x 64] sub-blocks
+constexpr int kDensBlkBytes = 8192;  // density head [16 x 256] 16-bit: four swizzled [16 x 64] sub-blocks
 constexpr int kMaskBytes = 4096;     // sign mask of one layer and tile: 128 rows x 256 bits
 constexpr int kHeadN = 16;           // UMMA N of the colour head (color_dim <= 3 rows used)
 
@@ -51,7 +52,11 @@ struct Arch {
   }
   // after the layers: one 4 KB stage with the colour head, W2 as a [16 x 128] K-major operand (two [16 x 64]
   // swizzled sub-blocks at byte offsets 0 and 2048; rows >= color_dim are zero)
-  __host__ __device__ int head_stage() const { return stage_offset(n_mma_layers()); }
+  // (before it: one 8 KB stage with the density head, w_d as row 0 of a [16 x 256] K-major operand, four [16 x 64]
+  // sub-blocks 2 KB apart: it is multiplied against the same activations as the colour hidden layer, into 16 accumulator
+  // columns that layer leaves free)
+  __host__ __device__ int density_stage() const { return stage_offset(n_mma_layers()); }
+  __host__ __device__ int head_stage() const { return density_stage() + 1; }
   __host__ __device__ int total_stages() const { return head_stage() + 1; }
 
   // true input / output widths of mma layer l

@@ -123,46 +123,6 @@ __device__ __forceinline__ void store_mask_half(uint8_t* mask_row, int half, con
   *reinterpret_cast<uint4*>(mask_row + half * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// last trunk layer: processes accumulator columns [c_lo, c_lo + 128) of one row: ReLU -> 16-bit -> activation blocks
-// (c_lo / 64, c_lo / 64 + 1), and the fp32 density head on the un-rounded activations
-template <int kFmt>
-__device__ __forceinline__ void epilogue_half_density(uint32_t t_addr, int c_lo, const float* __restrict__ wd,
-                                                      float& dens, uint32_t act_row, uint32_t swz, uint8_t* mask_row) {
-#pragma unroll 1
-  for (int cb = 0; cb < 4; cb += 2) {
-    uint32_t v[2][32];
-    tmem_ld32(t_addr + c_lo + cb * 32, v[0]);
-    tmem_ld32(t_addr + c_lo + cb * 32 + 32, v[1]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c0 = c_lo + (cb + h) * 32;
-      uint32_t pk[16];
-      uint32_t sign = 0u;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        // the bias is already in the accumulator (folded into the MMA)
-        const float x0 = fmaxf(__uint_as_float(v[h][j]), 0.f), x1 = fmaxf(__uint_as_float(v[h][j + 1]), 0.f);
-        const float x2 = fmaxf(__uint_as_float(v[h][j + 2]), 0.f), x3 = fmaxf(__uint_as_float(v[h][j + 3]), 0.f);
-        if (mask_row)
-          sign = push_sign(push_sign(push_sign(push_sign(sign, __uint_as_float(v[h][j])), __uint_as_float(v[h][j + 1])),
-                                     __uint_as_float(v[h][j + 2])), __uint_as_float(v[h][j + 3]));
-        const float4 w = __ldg(reinterpret_cast<const float4*>(wd + c0 + j));
-        dens = fmaf(x0, w.x, dens); dens = fmaf(x1, w.y, dens);
-        dens = fmaf(x2, w.z, dens); dens = fmaf(x3, w.w, dens);
-        pk[j / 2] = Half2Pack<kFmt>::pack(x0, x1);
-        pk[j / 2 + 1] = Half2Pack<kFmt>::pack(x2, x3);
-      }
-      const uint32_t blk = act_row + (c0 >> 6) * kBlkBytes;
-      const uint32_t u0 = ((c0 >> 5) & 1) * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        st_shared_v4(blk + (((u0 + i) ^ swz) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-      if (mask_row) *reinterpret_cast<uint32_t*>(mask_row + (c0 >> 5) * 4) = sign;
-    }
-  }
-}
-
 // Plain 256-wide layers (no head attached): the whole 128-column half is pulled out of TMEM with one wait, converted
 // (ReLU fused into the conversion), and only then `before_store` runs -- for half 0 that is the wait until this layer's
 // MMAs have stopped reading activation blocks 0,1 -- so the TMEM latency and the conversions sit in the shadow of
@@ -240,9 +200,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
   const uint32_t s_ring = smem_base + kSmemRing;
   const uint32_t s_bar = smem_base + kSmemBar;
   // barriers (8 B each): full[4], empty[4], then per tile g: half_full[g][2], blk01_free[g], epi_done[g][2],
-  // next_pair[g]; then the TMEM base address
+  // next_pair[g], dens_full[g]; then the TMEM base address
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * kRing, bar_hfull = s_bar + 16 * kRing,
-                 bar_b01 = bar_hfull + 32, bar_epi = bar_b01 + 16, bar_next = bar_epi + 32, s_tmem_ptr = bar_next + 16;
+                 bar_b01 = bar_hfull + 32, bar_epi = bar_b01 + 16, bar_next = bar_epi + 32, bar_dfull = bar_next + 16, s_tmem_ptr = bar_dfull + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -263,6 +223,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       mbar_init(bar_epi + 16 * g, 128);
       mbar_init(bar_epi + 16 * g + 8, 128);
       mbar_init(bar_next + 8 * g, 128);
+      mbar_init(bar_dfull + 8 * g, 1);
     }
     mbar_fence_init();
   }
@@ -297,15 +258,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
             if (++slot == kRing) { slot = 0; phase ^= 1; }
           }
         }
-        // colour head stage (4 KB)
-        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-        if (p.debug & 2) {
-          mbar_arrive(bar_full + 8 * slot);
-        } else {
-          mbar_arrive_expect_tx(bar_full + 8 * slot, kHeadBlkBytes);
-          bulk_g2s(s_ring + slot * kBlkBytes, p.wpack + (size_t)A.head_stage() * kBlkBytes, kHeadBlkBytes, bar_full + 8 * slot);
+        // density head stage (8 KB), then colour head stage (4 KB)
+        for (int hs = 0; hs < 2; ++hs) {
+          const uint32_t bytes = hs == 0 ? kDensBlkBytes : kHeadBlkBytes;
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          if (p.debug & 2) {
+            mbar_arrive(bar_full + 8 * slot);
+          } else {
+            mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+            bulk_g2s(s_ring + slot * kBlkBytes, p.wpack + (size_t)(A.density_stage() + hs) * kBlkBytes, bytes, bar_full + 8 * slot);
+          }
+          if (++slot == kRing) { slot = 0; phase ^= 1; }
         }
-        if (++slot == kRing) { slot = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -369,7 +333,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
               if (++slot == kRing) { slot = 0; phase ^= 1; }
               // activation blocks 0,1 are not read again in this layer after (last half, kb_free); layer 0 reads
               // only the embedding block, so they are free from its first MMA on
-              if (l == 0 ? (nh == 0 && kb == 0) : (nh == nnh - 1 && kb == kb_free)) umma_commit(my_b01);
+              // (the colour hidden layer is followed by the density head, which reads all four blocks again)
+              if (l != L - 1 && (l == 0 ? (nh == 0 && kb == 0) : (nh == nnh - 1 && kb == kb_free))) umma_commit(my_b01);
             }
             if (has_bias) {
               // + bias: embedding slice 3 (channel 63 == 1) x the [128 x 16] bias block
@@ -381,6 +346,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
             }
             umma_commit(my_hfull + 8 * nh);
             tr.log(l << 8 | 4 | nh);
+          }
+          if (l == L - 1) {
+            // density head: the same activations (last trunk output, blocks 0-3) x w_d -> 16 accumulator columns
+            // [144, 160) of the tile (the colour hidden layer is 128 wide and leaves the second half free)
+            constexpr uint32_t idesc_dens = umma_idesc(128, kHeadN, kFmt, 0, 0);
+            if (!waited1) {
+              mbar_wait(my_epi + 8, ed_phase1);
+              ed_phase1 ^= 1;
+              tc_fence_after();
+              waited1 = true;
+            }
+            mbar_wait(bar_full + 8 * slot, phase);
+            tc_fence_after();
+            const uint32_t d_dens = tmem_base + g * 256 + 144;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+              const uint64_t a_desc = umma_desc_kmajor(act_base + kb * kBlkBytes);
+              const uint64_t b_desc = umma_desc_kmajor(s_ring + slot * kBlkBytes + kb * 2048);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_dens, a_desc + 2 * k, b_desc + 2 * k, idesc_dens, (kb | k) != 0);
+              if (kb == 1) umma_commit(my_b01);  // blocks 0,1 are not read again
+            }
+            umma_commit(bar_empty + 8 * slot);
+            if (++slot == kRing) { slot = 0; phase ^= 1; }
+            umma_commit(bar_dfull + 8 * g);
           }
           if (!waited1) {
             mbar_wait(my_epi + 8, ed_phase1);
@@ -429,7 +419,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     const bool stash_leader = (warp - 2) % 4 == 0 && lane == 0;
     const int nfx = A.n_freq_xyz;
     const int blocks_per_tile = A.stash_blocks_per_tile();
-    uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0;
+    uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0, df_phase = 0;
     Tracer tr;
     tr.init(q == 0 && lane == 0 ? p.trace : nullptr, 2 + g);
     int l_emb_last = 0;  // last layer that reads the embedding block as an operand
@@ -522,13 +512,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         }
       }
 
-      float dens = 0.f;
       for (int l = 0; l < L; ++l) {
         if (A.merged(l)) continue;
         const bool is_color = (l == L - 1);
         const bool is_last_trunk = (l == L - 3);
         const float* bias = is_color ? p.dirbias + ray * kDirPad : p.aux + A.aux_bias(l);
-        const float* wd = p.aux + A.aux_wd();
         if (is_last_trunk) {  // the colour layer's per-ray bias row (512 B): pull it into L1 one layer ahead
           const float* row_bias = p.dirbias + ray * kDirPad;
 #pragma unroll
@@ -550,7 +538,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
             named_bar_sync(1 + g, 128);
           }
         };
-        const bool plain = !is_color && !is_last_trunk;
+        const bool plain = !is_color;
         // ReLU sign mask of this layer and row (training only): trunk layer l -> mask l, colour hidden -> mask n_layers
         uint8_t* mask_row = nullptr;
         if (kStash && tile_live)
@@ -562,9 +550,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         } else if (is_color) {
           before_store0();
           epilogue_color_hidden<kFmt>(t_row, bias, act_row, swz, mask_row);
-        } else {
-          before_store0();
-          epilogue_half_density<kFmt>(t_row, 0, wd, dens, act_row, swz, mask_row);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -577,10 +562,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tc_fence_after();
           tr.log(l << 8 | 4);
           if (p.debug & 1) {
-          } else if (!is_last_trunk)
+          } else
             epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, mask_row, [] {});
-          else
-            epilogue_half_density<kFmt>(t_row, 128, wd, dens, act_row, swz, mask_row);
           tc_fence_before();
           fence_proxy_async_smem();
         }
@@ -601,8 +584,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           }
           write_embedding(2 * (pair + gridDim.x) + g);
         }
-        if (is_last_trunk && valid) p.density[gidx] = dens + __ldg(p.aux + A.aux_bd());
         if (is_color) {
+          // density head: accumulator column 144 of the tile
+          mbar_wait(bar_dfull + 8 * g, df_phase);
+          df_phase ^= 1;
+          tc_fence_after();
+          uint32_t dv[4];
+          tmem_ld4(t_row + 144, dv);
+          tmem_ld_wait();
+          if (valid) p.density[gidx] = __uint_as_float(dv[0]) + __ldg(p.aux + A.aux_bd());
           // colour head: 16 accumulator columns at the start of the tile's second half (the first color_dim are real);
           // the next pair's embedding arrival (program order) covers the TMEM hand-over
           mbar_wait(my_hfull + 8, hf_phase1);

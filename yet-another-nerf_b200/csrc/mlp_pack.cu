@@ -67,16 +67,19 @@ __global__ void pack_weights_kernel(const Arch A, const float* __restrict__ para
     int l = 0, off = 0;
     while (l < L && s >= off + A.stages(l)) { off += A.stages(l); ++l; }
     if (l == L) {
-      // colour head stage: W2 [color_dim x hidden_dir] as a [16 x 128] K-major operand, sub-block kb at kb * 2048
+      // density head stage: w_d as row 0 of a [16 x 256] K-major operand (4 sub-blocks); colour head stage: W2
+      // [color_dim x hidden_dir] as a [16 x 128] operand (2 sub-blocks); sub-block kb at byte offset kb * 2048
+      const bool dens = s == A.density_stage();
       uint4 out = make_uint4(0u, 0u, 0u, 0u);
       size_t dst = (size_t)unit * 16;
-      if (unit < 256) {
+      if (unit < (dens ? 512 : 256)) {
         const int kb = unit >> 7, rr = (unit >> 3) & 15, uu = unit & 7;
         float w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int k = kb * 64 + uu * 8 + i;
-          w[i] = (rr < A.color_dim && k < A.hidden_dir) ? params[A.color2_w_offset() + (int64_t)rr * A.hidden_dir + k] : 0.f;
+          if (dens) w[i] = (rr == 0 && k < A.hidden_last) ? params[A.density_w_offset() + k] : 0.f;
+          else w[i] = (rr < A.color_dim && k < A.hidden_dir) ? params[A.color2_w_offset() + (int64_t)rr * A.hidden_dir + k] : 0.f;
         }
         out.x = Half2Pack<kFmt>::pack(w[0], w[1]);
         out.y = Half2Pack<kFmt>::pack(w[2], w[3]);
