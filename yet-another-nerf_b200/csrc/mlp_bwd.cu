@@ -44,6 +44,7 @@ struct BwdParams {
   int64_t n_points;
   int64_t R;
   int P;
+  int debug;  // YN_BWD_DEBUG bits >= 16 (timing experiments)
 };
 
 __device__ __forceinline__ void bwd_named_bar_sync(int id, int nthreads) {
@@ -533,21 +534,30 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
     acc_w2[0][i] = acc_w2[1][i] = acc_w2[2][i] = 0.f;
   }
   float acc_bd = 0.f, acc_b2 = 0.f;
+  // d(density) and d(pre-sigmoid colour) of one point of a tile; loaded one tile ahead so that this (dependent, three
+  // small arrays) global-load latency overlaps the previous tile's work
+  float nx_dd = 0.f, nx_ds[3] = {0.f, 0.f, 0.f};
+  auto fetch = [&](int64_t tile) {
+    nx_dd = 0.f;
+    nx_ds[0] = nx_ds[1] = nx_ds[2] = 0.f;
+    const int64_t gidx = tile * kTileM + t;
+    if (t < kTileM && tile < n_tiles && gidx < p.n_points) {
+      nx_dd = __ldg(p.d_density + gidx);
+      for (int c = 0; c < C; ++c) {
+        const float y = __ldg(p.rgb + gidx * C + c);
+        nx_ds[c] = __ldg(p.d_rgb + gidx * C + c) * y * (1.f - y);
+      }
+    }
+  };
+  fetch(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
+    if (p.debug & 16) fetch(tile);  // experiment: no prefetch
     if (t < kTileM) {
-      const int64_t gidx = tile * kTileM + t;
-      float dd = 0.f, ds[4] = {0.f, 0.f, 0.f, 0.f};
-      if (gidx < p.n_points) {
-        dd = p.d_density[gidx];
-        for (int c = 0; c < C; ++c) {
-          const float y = p.rgb[gidx * C + c];
-          ds[c] = p.d_rgb[gidx * C + c] * y * (1.f - y);
-        }
-      }
-      s_dd[t] = dd;
-      for (int c = 0; c < 4; ++c) s_ds[t][c] = ds[c];
+      s_dd[t] = nx_dd;
+      s_ds[t][0] = nx_ds[0]; s_ds[t][1] = nx_ds[1]; s_ds[t][2] = nx_ds[2]; s_ds[t][3] = 0.f;
     }
+    fetch(tile + gridDim.x);
     __syncthreads();
     const uint8_t* base = p.stash + (size_t)tile * blocks_per_tile * kBlkBytes;
     const uint8_t* feat = base + (size_t)A.stash_block_of_layer(n - 1) * kBlkBytes + unit_off;  // last trunk output
@@ -611,28 +621,37 @@ __global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
 }
 
 // per-ray direction part of the colour hidden layer: dW_c[:, H + k] += sum_rays (sum_samples dY[ray, s, :]) emb27[ray][k]
-// one warp per ray; lane owns 4 of the 128 hidden columns (one 8-byte load per sample)
+// one warp per ray; lane owns 4 of the 128 hidden columns (one 8-byte load per sample, 16 samples in flight).  The outer
+// product with the ray's 27 embedding channels is accumulated in REGISTERS over all rays of the warp (108 accumulators
+// per lane); the 8 warps of a block are folded through shared memory once at the end.  (Per-ray shared-memory atomics, the
+// first version, were the bottleneck: 3 456 of them per ray.)
 template <int kFmt>
 __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
-  __shared__ float s_acc[kDirPad * 28];  // [j][k], 27 direction-embedding channels (+pad)
+  constexpr int kE = 28;                 // 27 direction-embedding channels (+pad); check_arch: embed_dir <= 32, here <= 27
+  __shared__ float s_acc[kDirPad * kE];  // [j][k]
   const Arch& A = p.arch;
   const int n = A.n_layers;
-  const int ed = A.embed_dir();
+  const int ed = A.embed_dir() < kE ? A.embed_dir() : kE;
   const int blocks_per_tile = A.stash_blocks_per_tile();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < kDirPad * 28; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < kDirPad * kE; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const size_t layer_off = (size_t)A.stash_block_of_layer(n + 1) * kBlkBytes;
   const int c0 = lane * 4;  // columns c0..c0+3 live in one 16-byte unit
   const size_t col_off = (size_t)(c0 >> 6) * kBlkBytes + ((c0 & 7) << 1);
   const uint32_t unit = (c0 >> 3) & 7;
+  float acc[4][kE];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < kE; ++k) acc[i][k] = 0.f;
   for (int64_t ray = (int64_t)blockIdx.x * nw + wib; ray < p.R; ray += (int64_t)gridDim.x * nw) {
     float gsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int s0 = 0; s0 < p.P; s0 += 8) {
-      uint2 v[8];
+    for (int s0 = 0; s0 < p.P; s0 += 16) {
+      uint2 v[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const int64_t gidx = ray * p.P + min(s0 + i, p.P - 1);
         const int64_t t = gidx / kTileM;
         const uint32_t r = (uint32_t)(gidx % kTileM);
@@ -640,7 +659,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
                                                     (size_t)r * 128 + ((unit ^ (r & 7)) << 4)));
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 16; ++i) {
         if (s0 + i < p.P) {
           const float2 a = Half2Pack<kFmt>::unpack(v[i].x), b = Half2Pack<kFmt>::unpack(v[i].y);
           gsum[0] += a.x; gsum[1] += a.y; gsum[2] += b.x; gsum[3] += b.y;
@@ -660,12 +679,17 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
       else if (k < 6 * nf) e_mine = cosf(d[(k - 3 * nf) / nf] * exp2f((float)((k - 3 * nf) % nf)));
       else e_mine = d[k - 6 * nf];
     }
-    for (int k = 0; k < ed && k < 32; ++k) {
-      const float e = __shfl_sync(0xffffffffu, e_mine, k);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[(c0 + i) * 28 + k], gsum[i] * e);
+    for (int k = 0; k < kE; ++k) {
+      const float e = __shfl_sync(0xffffffffu, e_mine, k);  // 0 for k >= ed
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][k] = fmaf(gsum[i], e, acc[i][k]);
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < kE; ++k) atomicAdd(&s_acc[(c0 + i) * kE + k], acc[i][k]);
   __syncthreads();
   const int din = A.din(n + 1);
   float* W = p.grads + A.w_offset(n + 1);
@@ -674,7 +698,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
   for (int i0 = threadIdx.x; i0 < n_flush; i0 += blockDim.x) {
     const int i = i0 + rot < n_flush ? i0 + rot : i0 + rot - n_flush;
     const int j = i / ed, k = i % ed;
-    atomicAdd(W + (int64_t)j * din + A.hidden_last + k, s_acc[j * 28 + k]);
+    atomicAdd(W + (int64_t)j * din + A.hidden_last + k, s_acc[j * kE + k]);
   }
 }
 
@@ -744,16 +768,23 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
     if (first_use(reinterpret_cast<const void*>(wgrad)))
       cudaFuncSetAttribute(wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
     // YN_BWD_DEBUG (timing experiments only, wrong gradients; tools/bwd_split.sh): bit mask of kernels to skip
-    static const int skip = getenv("YN_BWD_DEBUG") ? atoi(getenv("YN_BWD_DEBUG")) : 0;
+    const int skip = p.debug;
     cudaMemsetAsync(p.tbuf, 0, kTbufBytes, stream);
     if (!(skip & 1)) dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
     if (!(skip & 2)) {
       wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
       mlp_bwd_inter_kernel<<<A.hidden_last + A.hidden_dir, 256, 0, stream>>>(p);
     }
-    if (!(skip & 4)) heads<<<(int)(n_tiles < 4 * sms ? n_tiles : 4 * sms), 256, 0, stream>>>(p);
+    // exactly one resident wave of head blocks (a partial second wave would run at a third of the occupancy)
+    static int heads_per_sm = 0;
+    if (heads_per_sm == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&heads_per_sm, heads, 256, 0);
+      if (heads_per_sm < 1) heads_per_sm = 1;
+    }
+    const int64_t heads_grid = (int64_t)heads_per_sm * sms;
+    if (!(skip & 4)) heads<<<(int)(n_tiles < heads_grid ? n_tiles : heads_grid), 256, 0, stream>>>(p);
     const int64_t ray_blocks = (p.R + 7) / 8;
-    if (!(skip & 8)) dir<<<(int)(ray_blocks < 2 * sms ? ray_blocks : 2 * sms), 256, 0, stream>>>(p);
+    if (!(skip & 8)) dir<<<(int)(ray_blocks < sms ? ray_blocks : sms), 256, 0, stream>>>(p);  // 254 registers: one block per SM
   };
   if (A.fmt == 1)
     run(mlp_bwd_dgrad_kernel<1>, mlp_bwd_wgrad_kernel<1>, mlp_bwd_heads_kernel<1>, mlp_bwd_dir_kernel<1>);
@@ -795,5 +826,7 @@ extern "C" int yn_mlp_bwd(const yn_mlp_arch* arch, const float* directions, cons
   p.n_points = R * P;
   p.R = R;
   p.P = P;
+  static const int debug = getenv("YN_BWD_DEBUG") ? atoi(getenv("YN_BWD_DEBUG")) : 0;
+  p.debug = debug;
   return ynb::launch_bwd(p, static_cast<cudaStream_t>(stream));
 }
