@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const Arch A, const float*
                                                      const float* __restrict__ directions,
                                                      float* __restrict__ dirbias, int64_t R) {
   constexpr int kRays = 32;
-  __shared__ float s_emb[kRays][33];
+  __shared__ __align__(16) float s_emb[kRays][32];  // rows read back as float4 broadcasts (a scalar read per FMA was LDS-bound)
   __shared__ float s_dir[kRays][3];
   const int ed = A.embed_dir();  // <= 32 (check_arch)
   const int nf = A.n_freq_dir;
@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const Arch A, const float*
     s_dir[j][0] = d[0]; s_dir[j][1] = d[1]; s_dir[j][2] = d[2];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kRays * ed; i += blockDim.x) {
-    const int r = i / ed, k = i % ed;
-    float e;
+  for (int i = threadIdx.x; i < kRays * 32; i += blockDim.x) {
+    const int r = i >> 5, k = i & 31;
+    float e = 0.f;  // channels >= embed_dir are zero
     if (k < 3 * nf) e = sinf(s_dir[r][k / nf] * exp2f((float)(k % nf)));
     else if (k < 6 * nf) e = cosf(s_dir[r][(k - 3 * nf) / nf] * exp2f((float)((k - 3 * nf) % nf)));
-    else e = s_dir[r][k - 6 * nf];
+    else if (k < ed) e = s_dir[r][k - 6 * nf];
     s_emb[r][k] = e;
   }
   __syncthreads();
@@ -218,8 +218,15 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const Arch A, const float*
     const int64_t ray = ray0 + r;
     if (ray >= R) break;
     float acc = bj;
+    const float4* e4 = reinterpret_cast<const float4*>(s_emb[r]);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) acc = fmaf(w[k], k < ed ? s_emb[r][k] : 0.f, acc);
+    for (int k = 0; k < 8; ++k) {  // channels >= embed_dir hold zeros
+      const float4 e = e4[k];
+      acc = fmaf(w[4 * k], e.x, acc);
+      acc = fmaf(w[4 * k + 1], e.y, acc);
+      acc = fmaf(w[4 * k + 2], e.z, acc);
+      acc = fmaf(w[4 * k + 3], e.w, acc);
+    }
     dirbias[ray * kDirPad + j] = acc;
   }
 }
