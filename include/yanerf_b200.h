@@ -78,10 +78,11 @@ typedef struct yn_mlp_arch {
  * (xyz_encoder.mlp.{l}.0.{weight,bias}, intermediate_linear, density_layer, color_layer.0, color_layer.2). */
 int64_t yn_mlp_param_count(const yn_mlp_arch* arch);
 int64_t yn_mlp_wpack_bytes(const yn_mlp_arch* arch); /* tensor-core weight image (forward + backward) */
-int64_t yn_mlp_aux_floats(const yn_mlp_arch* arch);  /* padded biases and the small fp32 heads */
-int64_t yn_mlp_stash_bytes(const yn_mlp_arch* arch, int64_t n_points); /* activations kept for backward */
+int64_t yn_mlp_aux_floats(const yn_mlp_arch* arch);  /* fp32: padded biases, head weights/biases, the product W_c[:, :H] W_i */
+int64_t yn_mlp_stash_bytes(const yn_mlp_arch* arch, int64_t n_points); /* 16-bit activations + ReLU sign masks kept for backward */
 
-/* fp32 master weights -> 16-bit swizzled tensor-core images + fp32 aux; run after every weight update */
+/* fp32 master weights -> 16-bit swizzled tensor-core images + fp32 aux; run after every weight update.  The image is not a
+ * per-layer copy: the linear intermediate layer is multiplied into the colour hidden layer (W_c[:, :H] W_i, rounded once). */
 int yn_mlp_pack_weights(const yn_mlp_arch* arch, const float* params, void* wpack, float* aux, void* stream);
 
 /* per-ray part of LinearWithRepeat (models/utils.py:207-211) + harmonic embedding of normalised
