@@ -514,7 +514,7 @@ __device__ __forceinline__ float half_bits_to_float(uint16_t bits) {
 // rows rg, rg+8, ... of every tile: a warp reads whole rows (4 x 128-byte lines), all loads of a tile are in flight
 // together; the 8 row groups are folded through shared memory once, at the end.
 template <int kFmt>
-__global__ void __launch_bounds__(256) mlp_bwd_heads_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(256, 2) mlp_bwd_heads_kernel(const BwdParams p) {
   __shared__ float s_dd[kTileM];
   __shared__ float s_ds[kTileM][4];
   __shared__ float s_red[8][kInner + 3 * kDirPad];
