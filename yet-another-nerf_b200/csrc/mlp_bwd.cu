@@ -298,7 +298,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         mbar_wait(my_b01, b01_phase);
         b01_phase ^= 1;
         tc_fence_after();
-        if (leader) bulk_wait_read<0>();
+        // the gradient-stash store that last read dY blocks 0,1 has finished reading: the head store for step 0 (the only
+        // group in flight), otherwise the previous step's blocks-0,1 group (its blocks-2,3 group, the most recent one, may
+        // still be in flight)
+        if (leader) {
+          if (st == 0) bulk_wait_read<0>();
+          else bulk_wait_read<1>();
+        }
         bwd_named_bar_sync(1 + g, 128);
         // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
         if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
@@ -306,10 +312,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         tc_fence_before();
         fence_proxy_async_smem();
         if (!last) mbar_arrive(my_epi);
+        // store blocks 0,1 right away: two 32 KB stores per step spread over time instead of one 64 KB burst
+        bwd_named_bar_sync(1 + g, 128);
+        uint8_t* gdst = gstash_tile + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
+        if (leader) {
+          if (tile_live) {
+            bulk_s2g(gdst, g_g, kBlkBytes);
+            bulk_s2g(gdst + kBlkBytes, g_g + kBlkBytes, kBlkBytes);
+          }
+          bulk_commit();
+        }
         // ---- half 1
         mbar_wait(my_hfull + 8, hf_phase1);
         hf_phase1 ^= 1;
         tc_fence_after();
+        if (leader) bulk_wait_read<1>();  // the previous step's blocks-2,3 store (most recent group: this step's blocks 0,1)
+        bwd_named_bar_sync(1 + g, 128);
         // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
         if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mk1, swz, dd, wd, g_row);
@@ -317,9 +335,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         fence_proxy_async_smem();
         if (!last) mbar_arrive(my_epi + 8);
         bwd_named_bar_sync(1 + g, 128);
-        if (leader && tile_live) {
-          uint8_t* dst = gstash_tile + (size_t)A.stash_block_of_layer(prev) * kBlkBytes;
-          for (int b = 0; b < 4; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, g_g + b * kBlkBytes, kBlkBytes);
+        if (leader) {
+          if (tile_live) {
+            bulk_s2g(gdst + 2 * kBlkBytes, g_g + 2 * kBlkBytes, kBlkBytes);
+            bulk_s2g(gdst + 3 * kBlkBytes, g_g + 3 * kBlkBytes, kBlkBytes);
+          }
           bulk_commit();
         }
       }

@@ -534,7 +534,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tc_fence_after();
           tr.log(l << 8 | 2);
           if (kStash) {
-            if (stash_leader) bulk_wait_read<0>();  // the previous layer's stash store has read the buffer
+            // the previous layer's stash store of blocks 0,1 has read the buffer (its store of blocks 2,3, the most
+            // recent group, may still be in flight)
+            if (stash_leader) bulk_wait_read<1>();
+            named_bar_sync(1 + g, 128);
+          }
+        };
+        auto before_store1 = [&] {
+          if (kStash) {  // ... and the one of blocks 2,3 (most recent group now: this layer's blocks 0,1)
+            if (stash_leader) bulk_wait_read<1>();
             named_bar_sync(1 + g, 128);
           }
         };
@@ -555,6 +563,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         fence_proxy_async_smem();
         mbar_arrive(my_epi);
         tr.log(l << 8 | 3);
+        if (kStash) {
+          // stash blocks 0,1 right away (half a layer earlier than blocks 2,3: the stores are spread over time instead of
+          // arriving as one 64 KB burst per layer)
+          named_bar_sync(1 + g, 128);
+          if (stash_leader && tile_live) {
+            uint8_t* dst = stash_tile + (size_t)A.stash_block_of_layer(l) * kBlkBytes;
+            bulk_s2g(dst, act_g, kBlkBytes);
+            bulk_s2g(dst + kBlkBytes, act_g + kBlkBytes, kBlkBytes);
+          }
+          if (stash_leader) bulk_commit();
+        }
         // ---- half 1: columns [128,256) -> blocks 2,3 (the colour hidden layer is 128 wide: nothing to do)
         if (!is_color) {
           mbar_wait(my_hfull + 8, hf_phase1);
@@ -563,7 +582,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tr.log(l << 8 | 4);
           if (p.debug & 1) {
           } else
-            epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, mask_row, [] {});
+            epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, mask_row, before_store1);
           tc_fence_before();
           fence_proxy_async_smem();
         }
@@ -612,14 +631,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
               }
           }
         }
-        if (kStash) {
+        if (kStash && !is_color) {
           named_bar_sync(1 + g, 128);
           if (stash_leader && tile_live) {
-            uint8_t* dst = stash_tile + (size_t)A.stash_block_of_layer(l) * kBlkBytes;
-            const int nblk = is_color ? 2 : 4;
-            for (int b = 0; b < nblk; ++b) bulk_s2g(dst + (size_t)b * kBlkBytes, act_g + b * kBlkBytes, kBlkBytes);
-            bulk_commit();
+            uint8_t* dst = stash_tile + (size_t)(A.stash_block_of_layer(l) + 2) * kBlkBytes;
+            bulk_s2g(dst, act_g + 2 * kBlkBytes, kBlkBytes);
+            bulk_s2g(dst + kBlkBytes, act_g + 3 * kBlkBytes, kBlkBytes);
           }
+          if (stash_leader) bulk_commit();
         }
       }
     }
