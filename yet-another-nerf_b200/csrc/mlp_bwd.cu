@@ -756,15 +756,25 @@ __global__ void __launch_bounds__(256) mlp_bwd_inter_kernel(const BwdParams p) {
       p.grads[A.b_offset(n) + o] += acc;
     }
   } else {
+    // row j of dW_c[:, :H] = sum_k T[j][k] W_i[o][k] + s[j] b_i[o]: the contraction runs along the fast axis of W_i, so W_i
+    // goes through shared memory in [256 o x 32 k] tiles (coalesced 128-byte row reads, conflict-free column reads)
     const int j = blockIdx.x - H;
-    if (t < H) s_row[t] = T[j * kInner + t];
-    __syncthreads();
-    if (t < H) {  // t = output feature o of the intermediate layer
-      float acc = svec[j] * bi[t];
-      const float* w = Wi + (int64_t)t * H;
-      for (int k = 0; k < H; ++k) acc = fmaf(s_row[k], w[k], acc);
-      p.grads[A.w_offset(n + 1) + (int64_t)j * dinc + t] += acc;
+    __shared__ float s_w[kInner][33];
+    s_row[t] = t < H ? T[j * kInner + t] : 0.f;
+    float acc = t < H ? svec[j] * bi[t] : 0.f;
+    const int w = t >> 5, l = t & 31;
+    for (int k0 = 0; k0 < H; k0 += 32) {
+      __syncthreads();
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int o = w * 32 + r;
+        s_w[o][l] = (o < H && k0 + l < H) ? Wi[(int64_t)o * H + k0 + l] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) acc = fmaf(s_row[k0 + kk], s_w[t][kk], acc);
     }
+    if (t < H) p.grads[A.w_offset(n + 1) + (int64_t)j * dinc + t] += acc;
   }
 }
 

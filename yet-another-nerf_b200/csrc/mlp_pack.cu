@@ -13,10 +13,10 @@
 namespace ynb {
 
 // W_ci = W_c[:, :H] W_i and b_ci = W_c[:, :H] b_i (fp32) into the aux buffer: the merged intermediate + colour hidden layer
-// (mlp_common.cuh).  Block jt owns 4 rows of W_c (kept in shared memory), thread k owns column k and walks the whole
+// (mlp_common.cuh).  Block jt owns one row of W_c (kept in shared memory), thread k owns column k and walks the whole
 // reduction in a fixed order: deterministic (the same weights always give the same image), coalesced reads of W_i.
 __global__ void __launch_bounds__(256) fuse_color_kernel(const Arch A, const float* __restrict__ params, float* __restrict__ aux) {
-  constexpr int kRows = 4;
+  constexpr int kRows = 1;  // 128 blocks: the kernel is latency-bound, parallelism matters more than reuse
   const int jt = blockIdx.x;
   const int n = A.n_layers, H = A.hidden_last, dinc = A.din(n + 1);
   const float* Wi = params + A.w_offset(n);
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) fuse_color_kernel(const Arch A, const flo
     s_wc[jj][t] = (j < A.hidden_dir && t < H) ? Wc[(int64_t)j * dinc + t] : 0.f;
   }
   __syncthreads();
-  float acc[kRows] = {0.f, 0.f, 0.f, 0.f};
+  float acc[kRows] = {0.f};
   if (t < H) {
 #pragma unroll 8
     for (int o = 0; o < H; ++o) {
@@ -240,7 +240,7 @@ extern "C" int yn_mlp_pack_weights(const yn_mlp_arch* arch, const float* params,
   const ynb::Arch A = ynb::arch_from_c(arch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n_units = A.total_stages_all() * 1024;
-  ynb::fuse_color_kernel<<<ynb::kDirPad / 4, 256, 0, st>>>(A, params, aux);
+  ynb::fuse_color_kernel<<<ynb::kDirPad, 256, 0, st>>>(A, params, aux);  // one block per row of W_c
   if (A.fmt == 1)
     ynb::pack_weights_kernel<1><<<(n_units + 255) / 256, 256, 0, st>>>(A, params, aux, static_cast<uint8_t*>(wpack), n_units);
   else
