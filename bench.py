@@ -96,7 +96,7 @@ class ClockSampler:
 
 
 def synthetic_inputs(rank: int):
-    from yanerf import synthetic as syn
+    from tools import synthetic as syn
 
     poses = syn.synth_camera(1, seed=rank, jitter=0.0 if rank == 0 else 0.05)
     focal = torch.full((1, 1), syn.LEGO_FOCAL)
@@ -105,7 +105,7 @@ def synthetic_inputs(rank: int):
 
 
 def build_lego_pipeline(device, n_rays=4096):
-    from yanerf.testing import build_pipeline, load_synth_nets
+    from tools.testing import build_pipeline, load_synth_nets
 
     pipe = build_pipeline(H, W, n_rays, N_FINE, 0.2, CHUNK).to(device)
     nets = load_synth_nets(pipe, seeds=(0, 1), gain=1.0)
@@ -117,8 +117,8 @@ def cpu_render_baseline(budget_s: float = 12.0):
     """Oracle render of consecutive reference-sized chunks (2045 rays) of the synthetic 800x800 image on all
     host threads; returns rays/s and a description of the sample."""
     from oracle import nerf_oracle as O
-    from yanerf import synthetic as syn
-    from yanerf.testing import LEGO_MLP  # noqa: F401
+    from tools import synthetic as syn
+    from tools.testing import LEGO_MLP  # noqa: F401
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)

@@ -42,7 +42,7 @@ def golden():
 
 
 def oracle_spec(H, W, n_fine, noise_std, chunk, min_depth=2.0, max_depth=6.0):
-    """The oracle's PipelineSpec matching `yanerf.testing.pipeline_cfg` (test infrastructure)."""
+    """The oracle's PipelineSpec matching `tools.testing.pipeline_cfg` (test infrastructure)."""
     from oracle import nerf_oracle as O
 
     return O.PipelineSpec(image_height=H, image_width=W, n_pts_fine=n_fine, density_noise_std_train=noise_std,

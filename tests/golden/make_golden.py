@@ -4,7 +4,7 @@ REFERENCE (/root/reference) on seeded inputs.  Run in the build container only:
     python tests/golden/make_golden.py
 
 The GPU box has no /root/reference; it only reads the committed *.npz files.
-Inputs are regenerated from seeds by `yanerf/synthetic.py` (loaded by path so the
+Inputs are regenerated from seeds by `tools/synthetic.py` (loaded by path so the
 reference's own `yanerf` package stays the one on sys.path) or stored beside the
 outputs when small.  Random draws are injected into the reference by replacing
 torch.multinomial / rand_like / randn_like / rand with queues that replay
@@ -29,7 +29,7 @@ ref_shims.install()
 sys.path.insert(0, REF)
 
 spec = importlib.util.spec_from_file_location(
-    "yn_synthetic", os.path.join(REPO, "yet-another-nerf_b200", "yanerf", "synthetic.py")
+    "yn_synthetic", os.path.join(REPO, "tools", "synthetic.py")
 )
 syn = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(syn)

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as O
-from yanerf import synthetic as syn
+from tools import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
@@ -229,7 +229,7 @@ MLPS_SHALLOW = {
 
 def _build_mlp(name, seed, gain, dtype):
     from yanerf.pipelines.models import MODELS
-    from yanerf.testing import LEGO_MLP
+    from tools.testing import LEGO_MLP
 
     spec, over = {**MLPS, **MLPS_SHALLOW}[name]
     mlp = MODELS.build({**LEGO_MLP, **over})
@@ -286,7 +286,7 @@ def test_mlp_forward_shapes_and_tails(R, P):
 
 def test_mlp_unsupported_configs_fail_loudly():
     from yanerf.pipelines.models import MODELS
-    from yanerf.testing import LEGO_MLP
+    from tools.testing import LEGO_MLP
 
     with pytest.raises(NotImplementedError):
         MODELS.build({**LEGO_MLP, "latent_dim": 2})

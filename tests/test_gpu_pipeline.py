@@ -6,10 +6,10 @@ import pytest
 import torch
 
 from oracle import nerf_oracle as O
-from yanerf import synthetic as syn
+from tools import synthetic as syn
 from yanerf.pipelines.utils import EvaluationMode, sample_grid, scatter_rays_to_image
 from conftest import oracle_spec
-from yanerf.testing import build_pipeline, load_synth_nets, pipeline_cfg
+from tools.testing import build_pipeline, load_synth_nets, pipeline_cfg
 from yanerf.utils.config import ConfigDict
 
 pytestmark = pytest.mark.gpu
@@ -126,7 +126,7 @@ def test_ray_sampler_shapes_and_ranges():
 def test_model_output_shapes():
     """Reference tests/test_models.py:19-55 (the latent_dim variant is outside the kernel family and raises)."""
     from yanerf.pipelines.models import MODELS
-    from yanerf.testing import LEGO_MLP
+    from tools.testing import LEGO_MLP
 
     mlp = MODELS.build(dict(LEGO_MLP)).to(DEV)
     o, d, z = torch.rand(2, 4, 5, 3, device=DEV), torch.rand(2, 4, 5, 3, device=DEV), torch.rand(2, 4, 5, 6, device=DEV)
@@ -142,7 +142,7 @@ def test_renderer_two_pass_same_model_runs():
     from yanerf.pipelines.models import MODELS
     from yanerf.pipelines.renderers import RENDERERS
     from yanerf.pipelines.utils import PartialFunctionWrapper
-    from yanerf.testing import LEGO_MLP
+    from tools.testing import LEGO_MLP
 
     mlp = PartialFunctionWrapper(MODELS.build(dict(LEGO_MLP))).to(DEV)
     ren = RENDERERS.build(dict(type="MultipassEmissionAbsorpsionRenderer", n_pts_per_ray_fine_training=4,

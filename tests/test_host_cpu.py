@@ -128,7 +128,7 @@ def test_registry_contract():
 
 
 def test_pipeline_builds_with_reference_state_dict_layout():
-    from yanerf.testing import build_pipeline
+    from tools.testing import build_pipeline
 
     pipe = build_pipeline(800, 800, 4096, 128, 0.2, 131072)
     sd = pipe.state_dict()
@@ -185,13 +185,51 @@ def test_sample_grid_scatter_and_metrics():
     assert ViewMetrics()(image_sampling_grid=grid, images=None, images_pred=img) == {}
 
 
-def test_lr_schedule_and_stats():
-    from yanerf.runners.apis import create_stats
-    from yanerf.runners.engine import exponential_lr
+def test_lr_schedule_matches_reference_fixture():
+    """tests/golden/lr_schedule.json: learning rates set by the REFERENCE's `create_lr_scheduler` +
+    `warmup_lr_scheduler` (runners/utils.py:65-109, called as in runners/apis.py:77-79) for the lego.yml runner values at
+    world sizes 1 and 8, a cosine variant and a no-linear-scale variant (tests/golden/make_checkpoint_fixture.py)."""
+    import json
 
-    assert exponential_lr(0, 5e-4, 5e-5, 200000) == 5e-4
-    assert abs(exponential_lr(200000, 5e-4, 5e-5, 200000) - 5e-5) < 1e-12
-    assert abs(exponential_lr(500, 5e-4, 5e-5, 200000, warmup_iters=1000, warmup_lr=1e-5) - (1e-5 + 4.9e-4 * 0.5)) < 1e-12
+    from yanerf.runners.engine import reference_lr, scaled_runner_config
+
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lr_schedule.json")))
+    for name, case in fx["cases"].items():
+        cfg = scaled_runner_config(case["runner"], case["world"], distributed=case["world"] > 1)
+        got = [reference_lr(it, **cfg) for it in fx["iters"]]
+        assert got == case["lr"], (name, [(i, a, b) for i, a, b in zip(fx["iters"], got, case["lr"]) if a != b])
+    lego = fx["cases"]["lego_world1"]
+    assert abs(lego["lr"][fx["iters"].index(200000)] - 7.924465962305567e-05) < 1e-18  # not the 5e-5 a (min/init)^t law gives
+    with pytest.raises(ValueError):
+        reference_lr(0, init_lr=1e-3, min_lr=1e-4, lr_decay_type="linear")
+
+
+def test_train_one_epoch_reads_the_reference_runner_keys():
+    """`train_one_epoch` takes the reference's runner config (init_lr, min_lr, lr_decay_*, warmup_*, linear_scale) and
+    hands `reference_lr(iter)` to every step; a config in another vocabulary is rejected."""
+    from yanerf.runners.apis import create_stats, train_one_epoch
+    from yanerf.runners.engine import reference_lr
+
+    class FakeTrainer:
+        world = 1
+
+        def __init__(self):
+            self.lrs = []
+            self.pipeline = torch.nn.Linear(1, 1)
+
+        def train_step(self, data, lr):
+            self.lrs.append(lr)
+            return {"objective": torch.tensor([0.5]), "loss_rgb_mse": torch.tensor([0.01])}
+
+    conf = dict(init_lr=5e-4, min_lr=5e-5, lr_decay_type="exponential", lr_decay_rate=0.1, lr_decay_iters=250000,
+                num_iters=200000, warmup_steps=1000, warmup_lr=1e-5, linear_scale=True, print_per_iter=100)
+    tr = FakeTrainer()
+    stats = train_one_epoch(tr, [{}] * 5, conf, epoch=2, iters_per_epoch=500)
+    assert tr.lrs == [reference_lr(1000 + i, **conf) for i in range(5)]
+    assert tr.lrs[0] == 5e-4 and tr.lrs[1] < 5e-4  # iteration 1000 is still a warm-up iteration (`<=`), 1001 decays
+    assert tr.init_lr == 5e-4 and abs(stats["loss_rgb_psnr"] - 20.0) < 1e-4
+    with pytest.raises(KeyError):
+        train_one_epoch(FakeTrainer(), [{}], dict(lr=1e-3, min_lr=1e-4, num_iters=10))
     st = create_stats({"loss_rgb_mse": torch.tensor([0.01, 0.01]), "objective": torch.tensor([0.5]), "rendered_images": torch.zeros(1)})
     assert abs(st["loss_rgb_psnr"] - 20.0) < 1e-4 and st["objective"] == 0.5 and "rendered_images" not in st
 
@@ -207,7 +245,7 @@ def test_state_dict_keys_and_parameter_order_match_reference_checkpoint():
     """tests/golden/checkpoint_layout.json is the layout of a checkpoint written by the REFERENCE
     (scripts/run.py:416-422) for the lego pipeline: same state-dict keys, order and shapes here, and the same
     `parameters()` order, because torch.optim.Adam's state is indexed by parameter position."""
-    from yanerf.testing import build_pipeline
+    from tools.testing import build_pipeline
 
     layout = _ckpt_layout()
     pipe = build_pipeline(8, 8, 16, 8, 0.0, 4096)
@@ -220,25 +258,28 @@ def test_fused_trainer_reads_and_writes_reference_checkpoints():
     """A checkpoint in the reference's layout (model + torch.optim.Adam state + epoch) resumes in FusedTrainer, and
     what FusedTrainer writes loads into a real torch.optim.Adam over the same module."""
     from yanerf.runners import FusedTrainer
-    from yanerf.testing import build_pipeline
+    from tools.testing import build_pipeline
 
     layout = _ckpt_layout()
     torch.manual_seed(3)
     src = build_pipeline(8, 8, 16, 8, 0.0, 4096)
-    opt = torch.optim.Adam(src.parameters(), lr=3e-4)  # a real Adam state: two steps on random gradients
+    # the reference builds its param groups with `init_lr` (create_param_groups, runners/utils.py:142-186); every
+    # scheduler reads param_group["init_lr"] after a resume
+    opt = torch.optim.Adam([{"params": src.parameters(), "lr": 3e-4, "init_lr": 5e-4}], lr=5e-4)  # two steps on random gradients
     for _ in range(2):
         for p in src.parameters():
             p.grad = torch.randn_like(p)
         opt.step()
     ckpt = {"model": {k: v.clone() for k, v in src.state_dict().items()}, "optimizer": opt.state_dict(), "epoch": 7}
     # the synthetic checkpoint has the structure recorded from the reference
-    assert set(ckpt["optimizer"]["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "amsgrad", "params"}
+    assert set(ckpt["optimizer"]["param_groups"][0]) == set(layout["optimizer"]["param_groups"][0])
+    assert "init_lr" in layout["optimizer"]["param_groups"][0]
     assert sorted(ckpt["optimizer"]["state"][0]) == sorted(layout["optimizer"]["state"]["0"])
 
     dst = build_pipeline(8, 8, 16, 8, 0.0, 4096)
     trainer = FusedTrainer(dst, lr=1.0)
     assert trainer.load_state_dict(ckpt) == 8  # resume epoch (run.py:176)
-    assert trainer.step_count == 2 and trainer.lr == 3e-4
+    assert trainer.step_count == 2 and trainer.lr == 3e-4 and trainer.init_lr == 5e-4
     for (n, p), q in zip(dst.named_parameters(), src.parameters()):
         assert torch.equal(p, q), n
         assert p.data_ptr() >= trainer.flat.data_ptr()  # still a view into the flat buffer
@@ -254,6 +295,8 @@ def test_fused_trainer_reads_and_writes_reference_checkpoints():
     again = torch.optim.Adam(build_pipeline(8, 8, 16, 8, 0.0, 4096).parameters(), lr=1.0)
     again.load_state_dict(out["optimizer"])
     assert again.param_groups[0]["lr"] == 3e-4
+    assert again.param_groups[0]["init_lr"] == 5e-4  # survives load_state_dict: the reference's schedulers find it
+    assert set(out["optimizer"]["param_groups"][0]) == set(layout["optimizer"]["param_groups"][0])
     for i, st in again.state_dict()["state"].items():
         assert float(st["step"]) == 2.0
         assert torch.equal(st["exp_avg"], ckpt["optimizer"]["state"][i]["exp_avg"])
@@ -261,6 +304,38 @@ def test_fused_trainer_reads_and_writes_reference_checkpoints():
     bad = {"model": ckpt["model"], "optimizer": {"state": {}, "param_groups": [{"params": [0, 1]}]}}
     with pytest.raises(ValueError, match="optimizer state for 2 parameters"):
         trainer.load_state_dict(bad)
+    # `lr_param_groups` checkpoints (several groups with their own learning rates) are rejected, not half-loaded
+    two = {"model": ckpt["model"], "optimizer": {"state": {}, "param_groups": [{"params": list(range(24))}, {"params": list(range(24, 48))}]}}
+    with pytest.raises(NotImplementedError, match="param groups"):
+        trainer.load_state_dict(two)
+
+
+def test_cuda_graph_mode_rejects_what_it_cannot_capture():
+    """graph mode must refuse, not silently mis-train: host-reduced batch tensors (LLFF depth bounds, masks),
+    scene_extent > 0, zero warm-up steps, and batches whose structure changes after capture."""
+    from yanerf.runners import FusedTrainer
+    from tools.testing import build_pipeline
+
+    pipe = build_pipeline(8, 8, 16, 8, 0.0, 4096)
+    with pytest.raises(ValueError, match="graph_warmup_steps"):
+        FusedTrainer(pipe, use_cuda_graph=True, graph_warmup_steps=0)
+    tr = FusedTrainer(pipe, use_cuda_graph=True)
+    batch = dict(poses=torch.zeros(1, 3, 4), focal_lengths=torch.ones(1, 1), image_rgb=torch.zeros(1, 8, 8, 3))
+    assert tr._graph_unsupported(batch) is None
+    assert "min_depth" in tr._graph_unsupported({**batch, "min_depth": torch.ones(1, 1)})
+    assert "mask" in tr._graph_unsupported({**batch, "mask": torch.ones(1, 8, 8)})
+    assert tr._graph_unsupported({**batch, "min_depth": 2.0}) is None  # python floats are fine (baked into the graph)
+    pipe.ray_sampler.scene_extent = 8.0
+    assert "scene_extent" in tr._graph_unsupported(batch)
+    pipe.ray_sampler.scene_extent = 0.0
+    tr._static_batch = {**batch, "min_depth": 2.0}
+    tr._check_static({**batch, "min_depth": 2.0})
+    with pytest.raises(ValueError, match="differs from the value captured"):
+        tr._check_static({**batch, "min_depth": 3.0})
+    with pytest.raises(ValueError, match="does not match the captured"):
+        tr._check_static({**batch, "min_depth": 2.0, "image_rgb": torch.zeros(1, 4, 8, 3)})
+    with pytest.raises(ValueError, match="keys changed"):
+        tr._check_static(batch)
 
 
 def test_device_scene_feed_matches_distributed_sampler():

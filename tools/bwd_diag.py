@@ -3,9 +3,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "yet-another-nerf_b200")); sys.path.insert(0, os.path.join(REPO, "tests"))
 import numpy as np, torch
 from oracle import nerf_oracle as O
-from yanerf import synthetic as syn
+from tools import synthetic as syn
 from yanerf.pipelines.models import MODELS
-from yanerf.testing import LEGO_MLP
+from tools.testing import LEGO_MLP
 DEV = "cuda"
 T = lambda a: torch.from_numpy(np.asarray(a))
 for dtype in ("bf16", "fp16"):

@@ -3,9 +3,9 @@ import os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "yet-another-nerf_b200"))
 import torch
-from yanerf import synthetic as syn
+from tools import synthetic as syn
 from yanerf.pipelines.utils import EvaluationMode
-from yanerf.testing import build_pipeline, load_synth_nets
+from tools.testing import build_pipeline, load_synth_nets
 dev = "cuda"
 pipe = build_pipeline(8, 8, 24, 64, 0.2, 64 * 9).to(dev)
 load_synth_nets(pipe, (1, 2), 1.0)

@@ -1,12 +1,12 @@
 """Helpers shared by tests, bench.py and smoke(): build a lego.yml-shaped pipeline at a small image size,
-load seeded synthetic weights.  (Nothing here touches oracle/: this is the product package.)"""
+load seeded synthetic weights.  (Test infrastructure: lives outside the product package; nothing here touches oracle/.)"""
 from __future__ import annotations
 
 from typing import Dict, List, Sequence
 
 import torch
 
-from yanerf import synthetic as syn
+from tools import synthetic as syn
 from yanerf.utils.config import ConfigDict
 
 LEGO_MLP = dict(type="NeRFMLP", n_layers=8, input_skips=[5], n_harmonic_functions_xyz=10,

@@ -6,6 +6,7 @@ libyanerf_b200.so; torch only owns the memory and the stream.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
@@ -38,16 +39,26 @@ class Profiler:
         return out
 
 
-def _call(name: str, *args) -> None:
+STREAM = object()  # placeholder argument: the current stream of the launch device, resolved inside `_call`
+
+
+def _call(name: str, *args, device=None) -> None:
+    """Launch one C-ABI entry point on `device`'s current stream (the tensors' device, which need not be torch's
+    current device).  Callers keep every converted operand in a local variable until this returns: the launch is
+    stream-ordered, so a temporary may only go back to the caching allocator after the kernel has been queued."""
     fn = getattr(N.lib(), name)
-    if Profiler.enabled:
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        rc = fn(*args)
-        e.record()
-        Profiler.records.append((name, s, e))
-    else:
-        rc = fn(*args)
+    guard = torch.cuda.device(device) if (device is not None and device.index is not None
+                                          and device.index != torch.cuda.current_device()) else contextlib.nullcontext()
+    with guard:
+        args = tuple(N.stream_ptr() if a is STREAM else a for a in args)
+        if Profiler.enabled:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            Profiler.records.append((name, s, e))
+        else:
+            rc = fn(*args)
     Profiler.launches += Profiler.KERNELS_PER_CALL.get(name, 1)
     N.check(rc)
 
@@ -84,12 +95,13 @@ def ray_bundle(
     directions = torch.empty(B, n_rays, 3, device=dev)
     lengths = torch.empty(B, n_rays, P, device=dev)
     xys = torch.empty(B, n_rays, 2, device=dev) if full else xy
-    _call("yn_ray_bundle", 
-            ctypes.c_void_p(poses.data_ptr()), poses.stride(0), poses.stride(1), N.ptr(focal), N.ptr(xy),
-            N.ptr(N.f32c(depths)), N.ptr(None if u is None else N.f32c(u)), N.ptr(origins), N.ptr(directions),
-            N.ptr(lengths), N.ptr(xys if full else None), B, n_rays, P, width, height, 1 if full else 0,
-            N.stream_ptr(),
-        )
+    depths = N.f32c(depths)
+    u = None if u is None else N.f32c(u)
+    _call("yn_ray_bundle",
+          ctypes.c_void_p(poses.data_ptr()), poses.stride(0), poses.stride(1), N.ptr(focal), N.ptr(xy),
+          N.ptr(depths), N.ptr(u), N.ptr(origins), N.ptr(directions),
+          N.ptr(lengths), N.ptr(xys if full else None), B, n_rays, P, width, height, 1 if full else 0,
+          STREAM, device=dev)
     return origins, directions, lengths, xys
 
 
@@ -99,7 +111,7 @@ def sample_pixels(seed: torch.Tensor, batch: int, n: int, width: int, height: in
     idx = torch.empty(batch, n, dtype=torch.int64, device=seed.device)
     xy = torch.empty(batch, n, 2, device=seed.device)
     _call("yn_sample_pixels", N.ptr(seed, torch.int64), N.ptr(idx, torch.int64), N.ptr(xy), batch, n, width, height,
-          N.stream_ptr())
+          STREAM, device=seed.device)
     return idx, xy
 
 
@@ -132,9 +144,8 @@ class MlpPlan:
 
     def pack(self, flat_params: torch.Tensor) -> None:
         assert flat_params.numel() == self.n_params
-        _call("yn_mlp_pack_weights", 
-                ctypes.byref(self.arch), N.ptr(flat_params), N.ptr(self.wpack, torch.uint8), N.ptr(self.aux), N.stream_ptr()
-            )
+        _call("yn_mlp_pack_weights", ctypes.byref(self.arch), N.ptr(flat_params), N.ptr(self.wpack, torch.uint8),
+              N.ptr(self.aux), STREAM, device=self.wpack.device)
 
 
 def mlp_forward_raw(
@@ -151,12 +162,12 @@ def mlp_forward_raw(
         return density, rgb
     dirbias = torch.empty(R, 128, device=dev)
     L = N.lib()
-    _call("yn_mlp_dirbias", ctypes.byref(plan.arch), N.ptr(flat_params), N.ptr(directions), N.ptr(dirbias), R, N.stream_ptr())
-    _call("yn_mlp_fwd", 
-            ctypes.byref(plan.arch), N.ptr(origins), N.ptr(directions), N.ptr(lengths), N.ptr(dirbias),
-            N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(density), N.ptr(rgb),
-            N.ptr(stash, torch.uint8), R, P, N.stream_ptr(),
-        )
+    _call("yn_mlp_dirbias", ctypes.byref(plan.arch), N.ptr(flat_params), N.ptr(directions), N.ptr(dirbias), R, STREAM,
+          device=dev)
+    _call("yn_mlp_fwd",
+          ctypes.byref(plan.arch), N.ptr(origins), N.ptr(directions), N.ptr(lengths), N.ptr(dirbias),
+          N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(density), N.ptr(rgb),
+          N.ptr(stash, torch.uint8), R, P, STREAM, device=dev)
     return density, rgb
 
 
@@ -195,11 +206,10 @@ class MlpFunction(torch.autograd.Function):
             d_rgb = N.f32c(d_rgb) if d_rgb is not None else torch.zeros_like(rgb)
             wbytes = L.yn_mlp_bwd_workspace_bytes(ctypes.byref(plan.arch), R * P)
             work = torch.empty(int(wbytes), dtype=torch.uint8, device=rgb.device)
-            _call("yn_mlp_bwd", 
-                    ctypes.byref(plan.arch), N.ptr(directions), N.ptr(rgb), N.ptr(d_density), N.ptr(d_rgb),
-                    N.ptr(flat_params), N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(ctx.stash, torch.uint8),
-                    N.ptr(work, torch.uint8), N.ptr(grads), R, P, N.stream_ptr(),
-                )
+            _call("yn_mlp_bwd",
+                  ctypes.byref(plan.arch), N.ptr(directions), N.ptr(rgb), N.ptr(d_density), N.ptr(d_rgb),
+                  N.ptr(flat_params), N.ptr(plan.wpack, torch.uint8), N.ptr(plan.aux), N.ptr(ctx.stash, torch.uint8),
+                  N.ptr(work, torch.uint8), N.ptr(grads), R, P, STREAM, device=rgb.device)
         ctx.stash = None
         return (None if direct else grads), None, None, None, None, None, None
 
@@ -239,10 +249,9 @@ class CompositeFunction(torch.autograd.Function):
         depths = torch.empty(R, 1, device=dev)
         opacities = torch.empty(R, 1, device=dev)
         weights = torch.empty(R, P, device=dev)
-        _call("yn_composite_fwd", 
-                ctypes.byref(cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
-                N.ptr(bg), N.ptr(features), N.ptr(depths), N.ptr(opacities), N.ptr(weights), R, P, C, N.stream_ptr(),
-            )
+        _call("yn_composite_fwd",
+              ctypes.byref(cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
+              N.ptr(bg), N.ptr(features), N.ptr(depths), N.ptr(opacities), N.ptr(weights), R, P, C, STREAM, device=dev)
         ctx.cfg = cfg
         ctx.has = (noise is not None, bg is not None)
         saved = [raw_density, rgb, lengths, directions] + ([noise] if noise is not None else []) + ([bg] if bg is not None else [])
@@ -262,12 +271,13 @@ class CompositeFunction(torch.autograd.Function):
             d_features = torch.zeros(R, C, device=rgb.device)
         d_sigma = torch.empty_like(raw_density)
         d_rgb = torch.empty_like(rgb)
-        opt = lambda t: None if t is None else N.f32c(t)
-        _call("yn_composite_bwd", 
-                ctypes.byref(ctx.cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
-                N.ptr(bg), N.ptr(N.f32c(d_features)), N.ptr(opt(d_depths)), N.ptr(opt(d_opacities)),
-                N.ptr(opt(d_weights)), N.ptr(d_sigma), N.ptr(d_rgb), R, P, C, N.stream_ptr(),
-            )
+        # converted gradients stay referenced until the launch is queued (see `_call`)
+        d_features, d_depths, d_opacities, d_weights = (None if t is None else N.f32c(t)
+                                                        for t in (d_features, d_depths, d_opacities, d_weights))
+        _call("yn_composite_bwd",
+              ctypes.byref(ctx.cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
+              N.ptr(bg), N.ptr(d_features), N.ptr(d_depths), N.ptr(d_opacities),
+              N.ptr(d_weights), N.ptr(d_sigma), N.ptr(d_rgb), R, P, C, STREAM, device=rgb.device)
         return d_sigma, d_rgb, None, None, None, None, None
 
 
@@ -320,10 +330,10 @@ def sample_pdf_merge(lengths: torch.Tensor, weights: torch.Tensor, n_new: int, u
         u = N.f32c(u)
         assert u.shape == (R, n_new), (u.shape, (R, n_new))
         stride = n_new
-    _call("yn_sample_pdf_merge", 
-            N.ptr(N.f32c(lengths)), N.ptr(N.f32c(weights)), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
-            N.ptr(flag, torch.int32), R, P, n_new, int(add_input_samples), N.stream_ptr(),
-        )
+    lengths, weights = N.f32c(lengths), N.f32c(weights)
+    _call("yn_sample_pdf_merge",
+          N.ptr(lengths), N.ptr(weights), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
+          N.ptr(flag, torch.int32), R, P, n_new, int(add_input_samples), STREAM, device=dev)
     return out, inds, flag
 
 
@@ -341,10 +351,10 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Opt
         u, stride = det_draws(n_samples, dev), 0
     else:
         u, stride = N.f32c(u), n_samples
-    _call("yn_sample_pdf", 
-            N.ptr(N.f32c(bins)), N.ptr(N.f32c(weights)), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
-            N.ptr(flag, torch.int32), R, nb, n_samples, N.stream_ptr(),
-        )
+    bins, weights = N.f32c(bins), N.f32c(weights)
+    _call("yn_sample_pdf",
+          N.ptr(bins), N.ptr(weights), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
+          N.ptr(flag, torch.int32), R, nb, n_samples, STREAM, device=dev)
     return out, inds, flag
 
 
@@ -352,13 +362,12 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Opt
 # optimizer
 # --------------------------------------------------------------------------- #
 def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-    _call("yn_adam_step", 
-            N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
-            int(step), grad_scale, N.stream_ptr(),
-        )
+    _call("yn_adam_step",
+          N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(), lr, beta1, beta2, eps,
+          int(step), grad_scale, STREAM, device=params.device)
 
 
 def adam_step_dev(params, grads, exp_avg, exp_avg_sq, state, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     """Adam with step / lr read from the device tensor `state` = [step, lr] (CUDA-graph friendly)."""
     _call("yn_adam_step_dev", N.ptr(params), N.ptr(grads), N.ptr(exp_avg), N.ptr(exp_avg_sq), params.numel(),
-          N.ptr(state), beta1, beta2, eps, grad_scale, N.stream_ptr())
+          N.ptr(state), beta1, beta2, eps, grad_scale, STREAM, device=params.device)

@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from yanerf.pipelines.utils import EvaluationMode
 
-from .engine import FusedTrainer, exponential_lr
+from .engine import FusedTrainer, reference_lr, scaled_runner_config
 
 
 def inference(model: torch.nn.Module, data: Dict[str, Any], evaluation_mode: EvaluationMode, compute_metrics: bool = True):
@@ -52,16 +52,25 @@ def enable_ray_sharding(model: torch.nn.Module, group=None) -> bool:
 
 def train_one_epoch(trainer: FusedTrainer, batches: Iterable[Dict[str, Any]], config: Dict[str, Any], epoch: int = 0,
                     iters_per_epoch: Optional[int] = None) -> Dict[str, float]:
-    """One pass over `batches` (dicts of device tensors keyed like the dataset NamedTuples)."""
-    world = trainer.world
-    lr, min_lr = config.get("lr", 5e-4) * world, config.get("min_lr", 5e-5) * world  # scripts/run.py:152-156
-    num_iters = config.get("num_iters", 200000)
+    """One pass over `batches` (dicts of device tensors keyed like the dataset NamedTuples).
+
+    `config` is the reference's runner config (configs/nerf/lego.yml:12-33): `init_lr`, `min_lr`, `lr_decay_type`,
+    `lr_decay_rate`, `lr_decay_iters`, `num_iters`, `warmup_steps`, `warmup_lr`, `linear_scale`.  The learning rate of
+    every iteration is the reference's (`reference_lr`: decay schedule, then the warm-up override while
+    `iter <= warmup_steps`, runners/apis.py:77-79), with `init_lr` / `min_lr` scaled by the world size when
+    `linear_scale` is set and a process group is initialised (scripts/run.py:152-156)."""
+    missing = [k for k in ("init_lr", "min_lr") if k not in config]
+    if missing:
+        raise KeyError(f"runner config lacks {missing} (reference keys: init_lr, min_lr, lr_decay_type, lr_decay_rate, "
+                       "lr_decay_iters, num_iters, warmup_steps, warmup_lr, linear_scale)")
+    distributed = dist.is_available() and dist.is_initialized()
+    cfg = scaled_runner_config(dict(config), trainer.world, distributed)
+    trainer.init_lr = cfg["init_lr"]  # written into checkpoints (the reference's param groups carry it)
     it = epoch * (iters_per_epoch or 0)
     trainer.pipeline.train()
     preds: Dict[str, Any] = {}
     for data in batches:
-        step_lr = exponential_lr(it, lr, min_lr, num_iters, config.get("warmup_steps", 0), config.get("warmup_lr", 0.0))
-        preds = trainer.train_step(data, lr=step_lr)
+        preds = trainer.train_step(data, lr=reference_lr(it, **cfg))
         it += 1
     return create_stats(preds)
 

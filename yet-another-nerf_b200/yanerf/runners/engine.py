@@ -9,6 +9,7 @@ The forward/backward itself is `NeRFPipeline.forward` + autograd, i.e. the kerne
 """
 from __future__ import annotations
 
+import math
 from typing import Any, Callable, Dict, List, Optional
 
 import torch
@@ -18,13 +19,35 @@ from yanerf import ops
 from yanerf.pipelines.utils import EvaluationMode
 
 
-def exponential_lr(it: int, lr: float, min_lr: float, num_iters: int, warmup_iters: int = 0, warmup_lr: float = 0.0) -> float:
-    """Learning-rate schedule of the reference runner (runners/utils.py:65-109): linear warm-up from
-    `warmup_lr`, then exponential decay lr -> min_lr over `num_iters`."""
-    if warmup_iters > 0 and it < warmup_iters:
-        return warmup_lr + (lr - warmup_lr) * it / warmup_iters
-    t = min(max(it, 0), num_iters) / max(num_iters, 1)
-    return lr * (min_lr / lr) ** t
+def reference_lr(it: int, *, init_lr: float, min_lr: float, lr_decay_type: str = "exponential", lr_decay_rate: float = 0.1,
+                 lr_decay_iters: int = 250000, num_iters: int = 200000, warmup_steps: int = 0, warmup_lr: float = 0.0,
+                 **_unused) -> float:
+    """Learning rate of iteration `it`, exactly as the reference runner sets it before every step
+    (runners/apis.py:77-79): the decay schedule first --
+      "exponential": `max(min_lr, init_lr * lr_decay_rate ** (it / lr_decay_iters))`   (runners/utils.py:82-86)
+      "cosine":      `(init_lr - min_lr) * 0.5 * (1 + cos(pi * (it / lr_decay_iters) / num_iters)) + min_lr`   (73-79)
+    -- then, while `it <= warmup_steps`, overwritten by the linear warm-up
+      `min(init_lr, warmup_lr + (init_lr - warmup_lr) * it / warmup_steps)`   (65-70).
+    Keyword names are the runner-config keys of configs/nerf/lego.yml:12-33."""
+    if lr_decay_type == "exponential":
+        lr = max(min_lr, init_lr * (lr_decay_rate ** (it / lr_decay_iters)))
+    elif lr_decay_type == "cosine":
+        lr = (init_lr - min_lr) * 0.5 * (1.0 + math.cos(math.pi * (it / lr_decay_iters) / num_iters)) + min_lr
+    else:
+        raise ValueError(f"lr_decay_type {lr_decay_type!r}")  # runners/utils.py:106-107
+    if warmup_steps > 0 and it <= warmup_steps:
+        lr = min(init_lr, warmup_lr + (init_lr - warmup_lr) * it / warmup_steps)
+    return lr
+
+
+def scaled_runner_config(config: Dict[str, Any], world_size: int, distributed: bool) -> Dict[str, Any]:
+    """`scripts/run.py:152-156`: with an initialised process group and `linear_scale` set, `init_lr` and `min_lr` are
+    multiplied by the world size (the warm-up start `warmup_lr` is not)."""
+    out = dict(config)
+    if distributed and out.get("linear_scale", False):
+        out["init_lr"] = out["init_lr"] * world_size
+        out["min_lr"] = out["min_lr"] * world_size
+    return out
 
 
 class FusedTrainer:
@@ -45,6 +68,10 @@ class FusedTrainer:
         self._static_batch: Dict[str, Any] = {}
         self._static_preds: Dict[str, Any] = {}
         self.lr, self.betas, self.eps = lr, betas, eps
+        self.init_lr = lr  # the reference's param groups carry `init_lr` (runners/utils.py:151,181); kept in checkpoints
+        if use_cuda_graph and graph_warmup_steps < 1:
+            raise ValueError("graph_warmup_steps must be >= 1: the first eager step fills the host-side caches "
+                             "(linspace rows, kernel attributes) that must not be part of the capture")
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.params: List[torch.nn.Parameter] = [p for p in pipeline.parameters() if p.requires_grad]
@@ -66,20 +93,25 @@ class FusedTrainer:
                 off += k
         self.step_count = 0
         self._state = torch.zeros(2, device=dev)  # [step, lr] read by yn_adam_step_dev
-        self._lr_host = torch.zeros(1).pin_memory() if dev.type == "cuda" else torch.zeros(1)
+        # pinned staging ring for the per-step learning rate: slot k is rewritten only after the copy that read it has
+        # completed (its event), so an in-flight non_blocking H2D copy never sees the next step's value
+        self._lr_ring = [[torch.zeros(1).pin_memory() if dev.type == "cuda" else torch.zeros(1), None] for _ in range(4)]
+        self._lr_slot = 0
         for m in pipeline.modules():  # O(n) graph-friendly pixel pick instead of torch.multinomial over H*W
             if hasattr(m, "fused_pixel_sampler"):
                 m.fused_pixel_sampler = True
-        self._flag_host, self._flag_event, self._flag_pending = None, None, False
         # no device->host sync inside the step: pixel-grid range checks move to the host (shapes) and the refiner's
-        # "Negative weights provided." flag is read once, after the whole step has been queued
-        pipeline.validate_pixel_grid = False
+        # "Negative weights provided." flag is ACCUMULATED on the device (flag |= this step's flags) and copied to pinned
+        # memory after every step; the host looks at copies whose event has completed, so a flag raised by step k can
+        # be reported late but never lost.  The switches are flipped only while a training step runs.
+        self._flag_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flag_slots = ([[torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()] for _ in range(8)]
+                            if dev.type == "cuda" else [])
+        self._flag_ring: List[int] = []  # indices of slots whose copy is in flight, oldest first
         self._refiners = [m for m in pipeline.modules() if hasattr(m, "check_weights")]
         for r in getattr(getattr(pipeline, "renderer", None), "_refiners", {}).values():
             if r not in self._refiners:
                 self._refiners.append(r)
-        for r in self._refiners:
-            r.check_weights = False
         self._mlps = [m for m in pipeline.modules() if hasattr(m, "invalidate_packed_weights")]
         # hand every NeRFMLP its slice of the flat buffers: one autograd leaf per network, gradients accumulated by
         # the kernels directly into flat_grad
@@ -112,12 +144,41 @@ class FusedTrainer:
         self._deferred_checks()
         return preds
 
+    class _NoHostSync:
+        """While a training step is being queued the pipeline must not read device values on the host: the pixel-grid
+        range assert and the refiner's `weights.min() <= 0` check are switched off (the latter is replaced by the
+        device flag) and restored afterwards, so evaluation keeps the reference's immediate errors."""
+
+        def __init__(self, trainer: "FusedTrainer") -> None:
+            self.t = trainer
+
+        def __enter__(self):
+            t = self.t
+            self.saved = (getattr(t.pipeline, "validate_pixel_grid", True), [r.check_weights for r in t._refiners])
+            t.pipeline.validate_pixel_grid = False
+            for r in t._refiners:
+                r.check_weights = False
+
+        def __exit__(self, *exc):
+            t = self.t
+            t.pipeline.validate_pixel_grid = self.saved[0]
+            for r, v in zip(t._refiners, self.saved[1]):
+                r.check_weights = v
+
+    def _forward_backward(self, batch: Dict[str, Any]) -> Dict[str, torch.Tensor]:
+        with FusedTrainer._NoHostSync(self):
+            preds = self.pipeline(**batch, evaluation_mode=EvaluationMode.TRAINING)
+            if "objective" not in preds:
+                raise KeyError("In train mode, but no loss (`objective`) is found.")  # runners/apis.py:90-91
+            preds["objective"].mean().backward()
+            for r in self._refiners:  # accumulate this step's "weight + 1e-5 <= 0 seen" flags on the device
+                if r.last_flag is not None:
+                    self._flag_dev.bitwise_or_(r.last_flag.reshape(1).to(torch.int32))
+        return preds
+
     def _eager_step(self, batch: Dict[str, Any], lr: Optional[float]) -> Dict[str, torch.Tensor]:
         self.zero_grad()
-        preds = self.pipeline(**batch, evaluation_mode=EvaluationMode.TRAINING)
-        if "objective" not in preds:
-            raise KeyError("objective")  # runners/apis.py:90-91
-        preds["objective"].mean().backward()
+        preds = self._forward_backward(batch)
         self.optimizer_step(lr)
         return preds
 
@@ -140,13 +201,16 @@ class FusedTrainer:
             torch.cuda.current_stream().wait_stream(self._side_stream)
             self._deferred_checks()
             return preds
-        self._lr_host[0] = self.lr if lr is None else lr
+        reason = self._graph_unsupported(batch)
+        if reason is not None:
+            raise NotImplementedError(f"use_cuda_graph: {reason}; construct FusedTrainer(use_cuda_graph=False) for this data")
         if self._graph is None:
             self._capture(batch)
+        self._check_static(batch)
         for k, v in batch.items():
             if torch.is_tensor(v):
                 self._static_batch[k].copy_(v, non_blocking=True)
-        self._state[1:2].copy_(self._lr_host, non_blocking=True)
+        self._stage_lr(self.lr if lr is None else lr)
         self._graph.replay()  # (the captured forward starts by re-packing the weight images from the flat buffer)
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -156,18 +220,55 @@ class FusedTrainer:
         self._deferred_checks()
         return self._static_preds
 
+    def _stage_lr(self, lr: float) -> None:
+        host, ev = self._lr_ring[self._lr_slot]
+        if ev is not None:
+            ev.synchronize()  # the copy that last read this slot (4 steps ago) has long completed
+        host[0] = lr
+        self._state[1:2].copy_(host, non_blocking=True)
+        if self.flat.device.type == "cuda":
+            if ev is None:
+                ev = self._lr_ring[self._lr_slot][1] = torch.cuda.Event()
+            ev.record()
+        self._lr_slot = (self._lr_slot + 1) % len(self._lr_ring)
+
+    def _graph_unsupported(self, batch: Dict[str, Any]) -> Optional[str]:
+        """Inputs whose handling needs a device->host read inside the step (`.item()` in the ray sampler:
+        ray_sampler.py:179, 280-283) cannot be captured: per-image depth bounds given as tensors (LLFF), sampling
+        masks, `scene_extent > 0`."""
+        for k in ("min_depth", "max_depth", "mask", "sampling_prob_mask", "fg_probability"):
+            if torch.is_tensor(batch.get(k)):
+                return f"batch field `{k}` is a tensor that the ray sampler reduces on the host"
+        rs = getattr(self.pipeline, "ray_sampler", None)
+        if rs is not None and float(getattr(rs, "scene_extent", 0.0) or 0.0) > 0:
+            return "ray_sampler.scene_extent > 0 derives the depth range from the camera position on the host"
+        return None
+
+    def _check_static(self, batch: Dict[str, Any]) -> None:
+        """Every replay must see the batch structure that was captured: same keys, tensor shapes / dtypes, and equal
+        non-tensor values (those were baked into the graph)."""
+        if set(batch) != set(self._static_batch):
+            raise ValueError(f"batch keys changed after graph capture: {sorted(batch)} vs {sorted(self._static_batch)}")
+        for k, v in batch.items():
+            ref = self._static_batch[k]
+            if torch.is_tensor(v):
+                if not torch.is_tensor(ref) or v.shape != ref.shape or v.dtype != ref.dtype:
+                    raise ValueError(f"batch field `{k}`: {tuple(v.shape)} {v.dtype} does not match the captured "
+                                     f"{tuple(ref.shape) if torch.is_tensor(ref) else type(ref).__name__}")
+            elif v != ref:
+                raise ValueError(f"batch field `{k}` = {v!r} differs from the value captured in the graph ({ref!r})")
+
     def _capture(self, batch: Dict[str, Any]) -> None:
         self._static_batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
         self._state[0] = float(self.step_count)
-        self._state[1:2].copy_(self._lr_host, non_blocking=True)
+        # whatever weight image an earlier (e.g. evaluation) forward left behind, the captured forward must START with
+        # the re-pack from the flat buffer: drop every cached image so that plan_for() packs inside the capture
+        self._invalidate()
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, stream=self._side_stream):
             self.flat_grad.zero_()
-            preds = self.pipeline(**self._static_batch, evaluation_mode=EvaluationMode.TRAINING)
-            if "objective" not in preds:
-                raise KeyError("objective")
-            preds["objective"].mean().backward()
+            preds = self._forward_backward(self._static_batch)
             if self.world == 1:
                 self._graph_optimizer()
             self._static_preds = {k: v.detach() if torch.is_tensor(v) else v for k, v in preds.items()}
@@ -181,31 +282,43 @@ class FusedTrainer:
                           self.betas[1], self.eps, grad_scale=1.0 / self.world)
 
     def _deferred_checks(self) -> None:
-        """The refiner's device flag of step k is copied to pinned memory asynchronously and examined at the end of
-        step k+1 (or by `finish()`), so the host never waits for the GPU inside a step."""
+        """Queue an asynchronous copy of the accumulated device flag into a fresh pinned slot and examine the slots
+        whose copies have completed.  The host never waits for the GPU inside a step; `finish()` waits."""
         self._raise_if_flagged(wait=False)
-        flags = [r.last_flag for r in self._refiners if r.last_flag is not None]
-        if flags:
-            if self._flag_host is None:
-                self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-                self._flag_event = torch.cuda.Event()
-            self._flag_host.copy_(torch.stack([f.reshape(()) for f in flags]).max().reshape(1), non_blocking=True)
-            self._flag_event.record()
-            self._flag_pending = True
+        if self.flat.device.type != "cuda":
+            if int(self._flag_dev.item()) != 0:
+                self._flag_dev.zero_()
+                raise ValueError("Negative weights provided.")
+            return
+        if len(self._flag_ring) == len(self._flag_slots):  # every slot in flight: wait for the oldest copy
+            self._raise_if_flagged(wait=True, only_oldest=True)
+        i = next(k for k in range(len(self._flag_slots)) if k not in self._flag_ring)
+        host, ev = self._flag_slots[i]
+        host.copy_(self._flag_dev, non_blocking=True)
+        ev.record()
+        self._flag_ring.append(i)
 
-    def _raise_if_flagged(self, wait: bool) -> None:
-        if not self._flag_pending:
-            return
-        if wait:
-            self._flag_event.synchronize()
-        elif not self._flag_event.query():
-            return
-        self._flag_pending = False
-        if int(self._flag_host.item()) != 0:
-            raise ValueError("Negative weights provided.")  # renderers/utils.py:123-124
+    def _raise_if_flagged(self, wait: bool, only_oldest: bool = False) -> None:
+        while self._flag_ring:
+            host, ev = self._flag_slots[self._flag_ring[0]]
+            if wait:
+                ev.synchronize()
+            elif not ev.query():
+                return
+            self._flag_ring.pop(0)
+            if int(host.item()) != 0:
+                torch.cuda.current_stream().synchronize()  # outstanding copies must not land in reused slots
+                self._flag_ring.clear()
+                self._flag_dev.zero_()  # reported: start over
+                raise ValueError("Negative weights provided.")  # renderers/utils.py:123-124
+            if only_oldest:
+                return
 
     def finish(self) -> None:
         """Wait for outstanding work and surface any deferred error."""
+        if self.flat.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        self._deferred_checks()
         self._raise_if_flagged(wait=True)
 
     def optimizer_step(self, lr: Optional[float] = None) -> None:
@@ -222,7 +335,9 @@ class FusedTrainer:
     # Wire format of the reference: {"model": pipeline.state_dict(), "optimizer": torch.optim.Adam.state_dict(),
     # "epoch": e}.  The optimizer state is indexed by parameter position in `model.parameters()` order, which is the
     # order of `self.params`; the moments are views into the flat buffers on the way out and copied in on the way in, so a
-    # reference checkpoint resumes here and a checkpoint written here resumes in the reference.
+    # reference checkpoint resumes here and a checkpoint written here resumes in the reference: the single param group
+    # carries `init_lr` like the reference's (`create_param_groups`, runners/utils.py:142-186), which every reference
+    # scheduler reads after `optimizer.load_state_dict` has replaced the groups with the saved ones.
     def optimizer_state_dict(self) -> Dict[str, Any]:
         state, off = {}, 0
         for i, p in enumerate(self.params):
@@ -230,7 +345,7 @@ class FusedTrainer:
             state[i] = {"step": torch.tensor(float(self.step_count)),
                         "exp_avg": self.exp_avg[off:off + k].view_as(p), "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p)}
             off += k
-        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+        group = {"lr": self.lr, "init_lr": self.init_lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
         return {"state": state if self.step_count > 0 else {}, "param_groups": [group]}
@@ -242,12 +357,17 @@ class FusedTrainer:
             self.step_count = int(opt["step"])
             return
         groups = opt["param_groups"]
+        if len(groups) > 1:
+            # runners/utils.py:153-186 (`lr_param_groups`): per-prefix learning rates.  One flat Adam launch has one lr.
+            raise NotImplementedError(f"checkpoint with {len(groups)} optimizer param groups (`lr_param_groups`): "
+                                      "FusedTrainer keeps a single learning rate for all parameters")
         order = [i for g in groups for i in g["params"]]
         if len(order) != len(self.params):
             raise ValueError(f"optimizer state for {len(order)} parameters, the pipeline has {len(self.params)}")
         if groups[0].get("weight_decay", 0) or groups[0].get("amsgrad", False):
             raise NotImplementedError("weight_decay / amsgrad checkpoints (the reference trains with plain Adam, run.py:159)")
         self.lr = float(groups[0].get("lr", self.lr))
+        self.init_lr = float(groups[0].get("init_lr", self.lr))
         self.betas = tuple(groups[0].get("betas", self.betas))
         self.eps = float(groups[0].get("eps", self.eps))
         state, off, steps = opt.get("state", {}), 0, set()
