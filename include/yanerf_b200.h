@@ -155,15 +155,16 @@ int yn_sample_pdf(const float* bins, const float* weights, const float* u, int64
 
 /* ------------------------------------------------------------------------------------------------
  * torch.optim.Adam step (scripts/run.py:159; weight_decay 0, amsgrad off) on flat buffers; grad_scale
- * multiplies the gradient first (1/world_size after a sum all-reduce, or 1/loss_scale).
+ * multiplies the gradient first (1/world_size after a sum all-reduce, or 1/loss_scale).  beta1 / beta2 are
+ * doubles: the bias corrections 1 - beta^step are evaluated in double precision like torch does.
  * ---------------------------------------------------------------------------------------------- */
 int yn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                 float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+                 double beta1, double beta2, float eps, int32_t step, float grad_scale, void* stream);
 
 /* Same update with the step counter and learning rate read from DEVICE memory (state[0] = step as float >= 1,
  * state[1] = lr): the launch can be part of a captured CUDA graph. */
 int yn_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                     const float* state, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                     const float* state, double beta1, double beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,9 @@
 TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this
 module: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker
-or as the timed CPU baseline, never as the thing shipped.
+or as the timed CPU baseline, never as the thing shipped.  (Every function follows the
+device of its inputs, so ``bench.py`` can also time the same restatement as
+"torch eager on the GPU": the stronger baseline of SURVEY 8(d) / BASELINE.md 3(c).)
 
 It is a from-scratch functional restatement (flat ``[R, P]`` tensors, explicit
 random draws passed in as arguments, no nn.Module state) of the reference's
@@ -116,7 +118,7 @@ def rays_from_xy(poses: Tensor, focal: Tensor, xy: Tensor, width: int, height: i
     pose = poses[:, :3, :4]
     origins = pose[:, None, :, 3].expand(B, n, 3)
     f = focal.reshape(B, 1)
-    cam = torch.stack(((xy[..., 0] - width * 0.5) / f, (xy[..., 1] - height * 0.5) / f, torch.ones(B, n)), dim=-1)
+    cam = torch.stack(((xy[..., 0] - width * 0.5) / f, (xy[..., 1] - height * 0.5) / f, torch.ones(B, n, device=xy.device)), dim=-1)
     directions = torch.sum(pose[:, None, :, :3] * cam[:, :, None, :], dim=-1)
     return origins, directions
 
@@ -138,7 +140,7 @@ def stratified_jitter(z: Tensor, u: Tensor) -> Tensor:
 def harmonic_embedding(x: Tensor, n_freq: int) -> Tensor:
     """sin | cos | x with frequencies 2^k, channel order x·f0..x·f{L-1}, y·…
     (`models/utils.py:74-78,90-103`)."""
-    freqs = 2.0 ** torch.arange(n_freq, dtype=torch.float32)
+    freqs = 2.0 ** torch.arange(n_freq, dtype=torch.float32, device=x.device)
     e = (x[..., None] * freqs).reshape(*x.shape[:-1], -1)
     return torch.cat((e.sin(), e.cos(), x), dim=-1)
 
@@ -210,7 +212,7 @@ def raymarch(
     weights = alpha * trans
     depths = (weights * lengths)[..., None].sum(dim=-2)
     if bg_color is None:
-        bg = torch.tensor(spec.bg_color, dtype=torch.float32).view(1, -1).expand(rgb.shape[0], -1)
+        bg = torch.tensor(spec.bg_color, dtype=torch.float32, device=rgb.device).view(1, -1).expand(rgb.shape[0], -1)
     else:
         bg = bg_color
     if not spec.hard_background:
@@ -244,7 +246,7 @@ def sample_pdf(
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
     if u is None:
-        u = torch.linspace(0.0, 1.0, n_samples, dtype=cdf.dtype)
+        u = torch.linspace(0.0, 1.0, n_samples, dtype=cdf.dtype).to(cdf.device)  # evaluated on the CPU like the reference
         u = u.expand(list(cdf.shape[:-1]) + [n_samples]).contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = (inds - 1).clamp(0)
@@ -365,11 +367,11 @@ def train_forward(
     """
     B = poses.shape[0]
     H, W = spec.image_height, spec.image_width
-    grid = xy_grid(H, W).reshape(1, H * W, 2).expand(B, -1, -1)
+    grid = xy_grid(H, W).to(poses.device).reshape(1, H * W, 2).expand(B, -1, -1)
     xy = torch.gather(grid, 1, draws["pix"][..., None].expand(-1, -1, 2))
     n = xy.shape[1]
     o, d = rays_from_xy(poses, focal, xy, W, H)
-    z = depth_linspace(spec.min_depth, spec.max_depth, spec.n_pts_coarse)[None, None].expand(B, n, -1)
+    z = depth_linspace(spec.min_depth, spec.max_depth, spec.n_pts_coarse).to(poses.device)[None, None].expand(B, n, -1)
     z = stratified_jitter(z, draws["u_strat"])
     passes = render_rays(nets, spec, o.reshape(-1, 3), d.reshape(-1, 3), z.reshape(B * n, -1), True, draws)
     gt = gather_pixels(image_rgb, xy)
@@ -395,12 +397,12 @@ def render_image(
     [start, end) of the flattened grid (used for bounded CPU timing)."""
     B = poses.shape[0]
     H, W = spec.image_height, spec.image_width
-    xy = xy_grid(H, W).reshape(1, H * W, 2).expand(B, -1, -1)
+    xy = xy_grid(H, W).to(poses.device).reshape(1, H * W, 2).expand(B, -1, -1)
     if ray_slice is not None:
         xy = xy[:, ray_slice[0]:ray_slice[1]]
     n = xy.shape[1]
     o, d = rays_from_xy(poses, focal, xy, W, H)
-    z = depth_linspace(spec.min_depth, spec.max_depth, spec.n_pts_coarse)[None, None].expand(B, n, -1)
+    z = depth_linspace(spec.min_depth, spec.max_depth, spec.n_pts_coarse).to(poses.device)[None, None].expand(B, n, -1)
     _, per = chunk_plan(n, spec.n_pts_coarse, spec.chunk_size_grid) if spec.chunk_size_grid > 0 else (1, n)
     acc: Dict[str, List[Tensor]] = {"features": [], "depths": [], "opacities": [], "coarse_features": []}
     for s in range(0, n, per):

@@ -463,3 +463,56 @@ def test_pixel_sampler_distinct_uniform():
     expected = 200 * 10 * 64 / 256
     chi2 = float(((counts - expected) ** 2 / expected).sum())
     assert chi2 < 255 + 6 * (2 * 255) ** 0.5, chi2  # mean 255, sigma ~22.6
+
+
+# --------------------------------------------------------------------------- fused Adam (row A)
+@pytest.mark.parametrize("world", [1, 8])
+def test_adam_kernel_vs_torch_and_oracle(world):
+    """`yn_adam_step` (host step / lr) and `yn_adam_step_dev` (step / lr in device memory) against torch.optim.Adam
+    (the optimizer scripts/run.py:159 builds) AND the oracle's `adam_step`, 10 steps on random flat buffers with a
+    changing learning rate; `grad_scale = 1 / world` models the mean of the DDP all-reduce (the kernels see the SUM of
+    the ranks' gradients).  Bound: rtol 1e-6 plus a few fp32 ulps of the largest gradient that entered the element (the
+    first moment is a signed sum: torch's `lerp_`, the oracle's `mul_().add_()` and the kernel's fused form round
+    differently by one ulp of the operands, which is unbounded RELATIVE to an element that cancels to near zero)."""
+    from yanerf import ops
+
+    n = 100_003
+    rs = np.random.RandomState(11 + world)
+    p0 = T((0.01 * rs.standard_normal(n)).astype(np.float32))  # small, so that one ulp of p is far below one update
+    grads = [T((rs.standard_normal(n) * 10.0 ** rs.uniform(-6, 0, size=n)).astype(np.float32)) for _ in range(10)]
+    lrs = [5e-4 * 0.9 ** k for k in range(10)]
+    # torch.optim.Adam on the CPU
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pt], lr=lrs[0])
+    # the oracle's restatement
+    po, mo, vo = p0.clone(), torch.zeros(n), torch.zeros(n)
+    # the two kernels
+    pk, mk, vk = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pd, md, vd = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    state = torch.zeros(2, device=DEV)
+    for k, (g, lr) in enumerate(zip(grads, lrs)):
+        opt.param_groups[0]["lr"] = lr
+        pt.grad = g.clone()
+        opt.step()
+        O.adam_step(po, g, mo, vo, k + 1, lr)
+        gsum = (g * world).to(DEV)  # what the all-reduce (SUM) leaves in the flat gradient buffer
+        ops.adam_step(pk, gsum, mk, vk, lr, k + 1, grad_scale=1.0 / world)
+        state[0], state[1] = float(k + 1), lr
+        ops.adam_step_dev(pd, gsum, md, vd, state, grad_scale=1.0 / world)
+    st = opt.state[pt]
+    gmax = torch.stack(grads).abs().max(dim=0)[0].double()
+    ulp = 2.0 ** -23
+
+    def close_ulp(got, ref, scale, what):
+        got, ref = got.detach().cpu().double(), ref.detach().double()
+        bad = (got - ref).abs() > 1e-6 * ref.abs() + 4 * ulp * scale
+        assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} off, max abs {float((got - ref).abs().max()):.3e}"
+
+    for name, (p_, m_, v_) in (("host-step kernel", (pk, mk, vk)), ("device-step kernel", (pd, md, vd))):
+        for ref_name, (pr, mr, vr) in (("torch.optim.Adam", (pt.detach(), st["exp_avg"], st["exp_avg_sq"])), ("oracle", (po, mo, vo))):
+            close_ulp(m_, mr, gmax, f"{name} exp_avg vs {ref_name}")
+            close_ulp(v_, vr, gmax * gmax, f"{name} exp_avg_sq vs {ref_name}")
+            # a parameter is the sum of 10 updates of size ~lr: compare the travelled distance, not the (O(1)) value;
+            # one ulp of the parameter itself (|p| ~ 1) is the floor of every single update
+            close(p_ - p0.to(DEV), pr - p0, 1e-5, 10 * ulp * (float(p0.abs().max()) + 5e-3), f"{name} parameter update vs {ref_name}")
+    assert torch.equal(pk, pd) or float((pk - pd).abs().max()) <= 1e-9

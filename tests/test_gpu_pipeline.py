@@ -20,7 +20,7 @@ def T(a):
     return torch.from_numpy(np.asarray(a))
 
 
-@pytest.mark.parametrize("tag,n_fine,std,gain", [("fern", 64, 0.0, 1.0), ("lego", 128, 0.2, 3.0)])
+@pytest.mark.parametrize("tag,n_fine,std,gain", [("fern", 64, 0.0, 1.0), ("lego1", 128, 0.2, 1.0), ("lego", 128, 0.2, 3.0)])
 @pytest.mark.parametrize("coalesce", [True, False])
 def test_eval_render_vs_reference_golden(golden, tag, n_fine, std, gain, coalesce):
     """Full-grid render, chunked (chunk_size_grid = 64*37 -> 9 chunks) and coalesced, vs the reference output."""
@@ -43,7 +43,11 @@ def test_eval_render_vs_reference_golden(golden, tag, n_fine, std, gain, coalesc
         # depth = sum(w * z) with z in [2, 6]: the 16-bit-operand density error moves it by O(1e-2) relative
         assert derr <= 0.12, derr
         assert abs(float(ev["loss_rgb_mse"].mean().cpu()) - float(g[f"{tag}_eval_loss_rgb_mse"].mean())) <= 1e-3
-    else:  # stress weights (see test_mlp_forward_golden)
+    else:
+        # "lego" tag = stress weights x3: raw densities reach O(1e3), the first sample with a positive density absorbs the
+        # whole ray, and WHICH sample that is flips with the last bit of the pre-activation: individual pixels differ by
+        # O(1) between ANY two arithmetics (fp32 vs fp64 of the reference itself included); only the mean is meaningful.
+        # The lego.yml configuration at a meaningful scale is the "lego1" case above (max abs <= 2e-3).
         assert float((ev["rendered_images"].cpu() - T(g[f"{tag}_eval_rendered_images"])).abs().mean()) <= 2e-2
     torch.testing.assert_close(ev["rendered_alpha_masks"].cpu(), T(g[f"{tag}_eval_rendered_alpha_masks"]), rtol=0, atol=1e-6)
     assert set(ev) >= {"loss_rgb_huber", "loss_rgb_mse", "loss_prev_stage_rgb_huber", "loss_prev_stage_rgb_mse",
@@ -185,7 +189,7 @@ def inject_draws(multinomial, rand, randn_like):
         assert not v, f"unused injected draws for {k}"
 
 
-@pytest.mark.parametrize("tag,n_fine,std,gain", [("fern", 64, 0.0, 1.0), ("lego", 128, 0.2, 3.0)])
+@pytest.mark.parametrize("tag,n_fine,std,gain", [("fern", 64, 0.0, 1.0), ("lego1", 128, 0.2, 1.0), ("lego", 128, 0.2, 3.0)])
 def test_train_forward_backward_vs_reference_golden(golden, tag, n_fine, std, gain):
     """TRAINING forward with the reference's draws replayed: losses vs the unmodified reference (golden), then
     backward: gradient summaries vs the reference's autograd."""
@@ -210,16 +214,48 @@ def test_train_forward_backward_vs_reference_golden(golden, tag, n_fine, std, ga
         err = float((preds["rendered_images"].cpu() - T(g[f"{tag}_train_rendered_images"])).abs().max())
         assert err <= 4e-3, err  # bf16 operands in training
     preds["objective"].mean().backward()
+    # Every one of the 2 x 24 parameter tensors against the reference's autograd (golden summaries: sum, sum|.|, L2 norm;
+    # three tensors in full).  The kernels run the layers with bf16 operands (8-bit mantissa) where the reference runs
+    # fp32, so a fraction of the ReLU units has the opposite sign (test_mlp_backward_vs_oracle_autograd quantifies it per
+    # layer).  Bounds at xavier scale ("fern", "lego1"): per-tensor L2 norm and sum|.| within 2 %, the signed sum within
+    # 2 % of sum|.|; the density head (a strongly cancelling sum of d(loss)/d(sigma) over all points of all rays) within
+    # 6 %; full tensors cos >= 0.985.  The x3 stress weights ("lego") are chaotic (see the eval test): gradients there
+    # are only required to be finite.
+    if gain != 1.0:
+        for fn in pipe.implicit_functions:
+            for name, p in fn._fn.named_parameters():
+                assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        return
+    k_norm, k_cos = 0.02, 0.985
+    worst = dict(norm=0.0, l1=0.0, sum=0.0)
+    failures = []
     for k, fn in enumerate(pipe.implicit_functions):
         for name, p in fn._fn.named_parameters():
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
-        gw = fn._fn.density_layer.weight.grad.cpu()
-        ref = T(g[f"{tag}_grad{k}_full_density_w"])
-        cos = float((gw * ref).sum() / (gw.norm() * ref.norm()).clamp_min(1e-30))
-        print(tag, k, "density_w grad cos", cos, float(gw.norm()), float(ref.norm()))
-        if gain == 1.0:
-            assert cos >= 0.98, cos
-            assert abs(float(gw.norm()) / float(ref.norm()) - 1) <= 0.1
+            gk = p.grad.detach().cpu().double().reshape(-1)
+            ref = T(g[f"{tag}_grad{k}_{name}"]).double()
+            rsum, rl1, rnorm = float(ref[0]), float(ref[1]), float(ref[2])
+            if rnorm < 1e-12:
+                assert float(gk.norm()) < 1e-9, name
+                continue
+            e_norm = abs(float(gk.norm()) / rnorm - 1)
+            e_l1 = abs(float(gk.abs().sum()) / rl1 - 1)
+            e_sum = abs(float(gk.sum()) - rsum) / rl1
+            print(f"  {tag} net{k} {name:36s} norm {rnorm:9.3e} dev {e_norm:7.4f}  sum|.| dev {e_l1:7.4f}  sum dev/sum|.| {e_sum:7.4f}")
+            worst = dict(norm=max(worst["norm"], e_norm), l1=max(worst["l1"], e_l1), sum=max(worst["sum"], e_sum))
+            tol = 3 * k_norm if name.startswith("density_layer") else k_norm
+            if not (e_norm <= tol and e_l1 <= tol and e_sum <= tol):
+                failures.append((tag, k, name, round(e_norm, 4), round(e_l1, 4), round(e_sum, 4)))
+        m = fn._fn
+        for key, t in (("full_density_w", m.density_layer.weight), ("full_color2_w", m.color_layer[2].weight),
+                       ("full_l0_b", m.xyz_encoder.mlp[0][0].bias)):
+            gw, ref = t.grad.cpu().double().reshape(-1), T(g[f"{tag}_grad{k}_{key}"]).double().reshape(-1)
+            cos = float((gw * ref).sum() / (gw.norm() * ref.norm()).clamp_min(1e-30))
+            print(f"  {tag} net{k} {key}: cos {cos:.5f}, norm ratio {float(gw.norm() / ref.norm()):.4f}")
+            if cos < k_cos:
+                failures.append((tag, k, key, "cos", round(cos, 5)))
+    print(tag, "worst relative deviations over all 48 gradient tensors:", worst)
+    assert not failures, failures
 
 
 def test_fused_trainer_converges_like_reference_runner():
@@ -236,12 +272,12 @@ def test_fused_trainer_converges_like_reference_runner():
     batch = dict(poses=syn.synth_camera(1, seed=0).to(DEV), focal_lengths=torch.full((1, 1), 2.0, device=DEV),
                  image_rgb=torch.rand(1, 2, 2, 3, device=DEV))
     first = None
-    from yanerf.runners.engine import exponential_lr
+    from yanerf.runners.engine import reference_lr
 
     for it in range(200):
         # the runner's exponential schedule (runners/utils.py:65-109); a constant 5e-3 spikes now and then on this
         # 4-ray problem, whatever the arithmetic
-        preds = trainer.train_step(batch, lr=exponential_lr(it, 5e-3, 5e-4, 200))
+        preds = trainer.train_step(batch, lr=reference_lr(it, init_lr=5e-3, min_lr=5e-4, lr_decay_rate=0.1, lr_decay_iters=200))
         if first is None:
             first = float(preds["objective"].detach().mean())
     with torch.no_grad():
@@ -319,6 +355,54 @@ def test_full_size_render_properties():
     dd = d.reshape(-1, 3)
     f1, f2, f12 = (ops.composite(sig, c, zf, dd, cfg)[0] for c in (c1, c2, 2 * c1 + 3 * c2))
     torch.testing.assert_close(f12, 2 * f1 + 3 * f2, rtol=1e-5, atol=1e-5)
+    # one reference-sized chunk (2045 rays: chunk 150 of the 313 the reference would loop over) against the CPU oracle
+    nets = [{k: v.detach().cpu() for k, v in fn._fn.state_dict().items()} for fn in pipe.implicit_functions]
+    n_chunks, per = O.chunk_plan(H * W, 64, 131072)
+    assert (n_chunks, per) == (313, 2045)
+    s0 = 150 * per
+    ref = O.render_image(nets, oracle_spec(H, W, 128, 0.2, 131072), poses.cpu(), focal.cpu(), ray_slice=(s0, s0 + per))
+    got = a["rendered_images"].reshape(1, H * W, 3)[:, s0:s0 + per].cpu()
+    err = float((got - ref["features"]).abs().max())
+    print(f"800x800 lego render, chunk 150 ({per} rays) vs oracle: max abs rgb err {err:.2e}")
+    assert err <= 2e-3, err
+
+
+def test_trained_scale_render_vs_oracle():
+    """SURVEY 7-C / VERDICT r1: the 2e-3 bound on TRAINED weights, not only on xavier-scale ones.  The lego.yml
+    architecture (64 + 128 samples, density noise 0.2) is trained for 400 fused steps on an analytic 8-view scene (a shaded
+    sphere), then one whole 48 x 48 view (2304 rays > one reference chunk of 2045) is rendered by the kernels (fp16
+    operands, the evaluation default) and by the CPU oracle (fp32) from the SAME trained weights."""
+    from yanerf.runners import FusedTrainer
+
+    torch.manual_seed(3)
+    H = W = 48
+    n_views, focal = 8, 60.0
+    pipe = build_pipeline(H, W, 1024, 128, 0.2, 131072).to(DEV)
+    poses = syn.orbit_cameras(n_views)
+    images = syn.sphere_scene_images(poses, focal, H, W)
+    trainer = FusedTrainer(pipe, lr=5e-4)
+    fl = torch.full((1, 1), focal, device=DEV)
+    for it in range(400):
+        v = it % n_views
+        trainer.train_step(dict(poses=poses[v:v + 1].to(DEV), focal_lengths=fl, image_rgb=images[v:v + 1].to(DEV)))
+    trainer.finish()
+    nets = [{k: v.detach().cpu().clone() for k, v in fn._fn.state_dict().items()} for fn in pipe.implicit_functions]
+    scale = max(float(sd["density_layer.weight"].abs().max()) for sd in nets)
+    with torch.no_grad():
+        ev = pipe(poses=poses[:1].to(DEV), focal_lengths=fl, image_rgb=images[:1].to(DEV), evaluation_mode=EvaluationMode.EVALUATION)
+        ref = O.render_image(nets, oracle_spec(H, W, 128, 0.2, 131072), poses[:1], torch.full((1, 1), focal))
+    got = ev["rendered_images"].reshape(1, H * W, 3).cpu()
+    err = (got - ref["features"]).abs()
+    mse = float(((got - ref["features"]) ** 2).mean())
+    psnr_vs_oracle = -10.0 * np.log10(max(mse, 1e-20))
+    psnr_vs_gt = -10.0 * np.log10(float(((ref["features"] - images[:1].reshape(1, H * W, 3)) ** 2).mean()))
+    print(f"trained-scale: oracle-vs-truth PSNR {psnr_vs_gt:.1f} dB; kernel-vs-oracle max abs {float(err.max()):.2e}, "
+          f"mean {float(err.mean()):.2e}, PSNR {psnr_vs_oracle:.1f} dB; max |w_density| {scale:.2f}")
+    assert psnr_vs_gt > 14.0, "the training did not move the weights away from their initial scale"
+    assert float(err.max()) <= 2e-3, float(err.max())
+    assert psnr_vs_oracle >= 55.0, psnr_vs_oracle
+    derr = float((ev["rendered_depths"].reshape(1, H * W, 1).cpu() - ref["depths"]).abs().max())
+    assert derr <= 0.05, derr
 
 
 def test_training_fits_a_synthetic_image():
@@ -494,7 +578,8 @@ def test_runner_epoch_loop_on_device_feed():
     feed = DeviceSceneFeed(syn.synth_camera(1, seed=0, jitter=0.0).expand(n, -1, -1), 25.0, img[None].expand(n, -1, -1, -1),
                            DEV, shuffle=True, seed=1)
     trainer = FusedTrainer(pipe, lr=5e-4, use_cuda_graph=True)
-    conf = dict(lr=1e-3, min_lr=1e-4, num_iters=120)
+    conf = dict(init_lr=1e-3, min_lr=1e-4, lr_decay_type="exponential", lr_decay_rate=0.1, lr_decay_iters=120, num_iters=120,
+                warmup_steps=0, warmup_lr=0.0, linear_scale=True)
     first = train_one_epoch(trainer, feed, conf, epoch=0, iters_per_epoch=len(feed))
     for epoch in range(1, 20):
         feed.set_epoch(epoch)

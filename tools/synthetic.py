@@ -80,3 +80,38 @@ def synth_draws(batch: int, n_rays: int, n_pixels: int, n_coarse: int, n_fine: i
 
 LEGO_FOCAL = 1111.111
 FERN_FOCAL = 407.6
+
+
+def orbit_cameras(n: int, radius: float = 4.0, elevation: float = 0.15) -> torch.Tensor:
+    """`n` camera-to-world poses [n,3,4] on a circle around the origin, looking at it (x right, y down, z forward:
+    the convention of the reference's README.md:99-103)."""
+    poses = []
+    for i in range(n):
+        th = 2.0 * math.pi * i / n
+        c = np.array([radius * math.sin(th), -radius * math.sin(elevation), -radius * math.cos(th)])
+        fwd = -c / np.linalg.norm(c)
+        right = np.cross(np.array([0.0, 1.0, 0.0]), fwd)
+        right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        poses.append(np.concatenate([np.stack([right, down, fwd], axis=1), c[:, None]], axis=1))
+    return torch.from_numpy(np.stack(poses).astype(np.float32))
+
+
+def sphere_scene_images(poses: torch.Tensor, focal: float, height: int, width: int, radius: float = 1.0) -> torch.Tensor:
+    """Analytic multi-view ground truth [n,H,W,3]: a unit sphere at the origin whose colour is 0.5 + 0.5 * normal, on a
+    black background, seen through the pinhole model of `_xy_to_ray_bundle` (ray_sampler.py:297-312)."""
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float32), torch.arange(width, dtype=torch.float32), indexing="ij")
+    dcam = torch.stack(((xs - width / 2) / focal, (ys - height / 2) / focal, torch.ones_like(xs)), dim=-1)  # [H,W,3]
+    out = []
+    for pose in poses:
+        rot, o = pose[:, :3], pose[:, 3]
+        d = dcam @ rot.T
+        a = (d * d).sum(-1)
+        b = 2.0 * (d * o).sum(-1)
+        c = float((o * o).sum()) - radius * radius
+        disc = b * b - 4 * a * c
+        hit = disc > 0
+        t = (-b - torch.sqrt(disc.clamp_min(0.0))) / (2 * a)
+        normal = (o + t[..., None] * d) / radius
+        out.append(torch.where(hit[..., None], 0.5 + 0.5 * normal, torch.zeros(3)))
+    return torch.stack(out).float()

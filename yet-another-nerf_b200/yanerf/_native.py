@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 from typing import Optional
 
 import torch
@@ -69,8 +69,8 @@ SYMBOLS = {
     "yn_composite_bwd": (c_int, [POINTER(MarchCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "yn_sample_pdf_merge": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "yn_sample_pdf": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, _P]),
-    "yn_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int32, c_float, _P]),
-    "yn_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P]),
+    "yn_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_double, c_double, c_float, c_int32, c_float, _P]),
+    "yn_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, c_double, c_double, c_float, c_float, _P]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
