@@ -121,13 +121,18 @@ typedef struct yn_march_cfg {
   float bg_const[4];
 } yn_march_cfg;
 
+/* noise: [R,P] N(0,1) draws (the reference's randn_like, lines 203-207) or NULL; with noise == NULL, rng_state != NULL and
+ * cfg->density_noise_std > 0 the draws are generated in the kernel (see "in-kernel draws" below), identically in
+ * yn_composite_fwd and yn_composite_bwd of the same step. */
 int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_density, const float* rgb, const float* lengths,
-                     const float* directions, const float* noise, const float* bg, float* features,
-                     float* depths, float* opacities, float* weights, int64_t R, int P, int C, void* stream);
+                     const float* directions, const float* noise, const int64_t* rng_state, int rng_site,
+                     const float* bg, float* features, float* depths, float* opacities, float* weights, int64_t R,
+                     int P, int C, void* stream);
 
 /* analytic backward (autograd of the same lines); d_depths / d_opacities / d_weights may be NULL */
 int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_density, const float* rgb, const float* lengths,
-                     const float* directions, const float* noise, const float* bg, const float* d_features,
+                     const float* directions, const float* noise, const int64_t* rng_state, int rng_site,
+                     const float* bg, const float* d_features,
                      const float* d_depths, const float* d_opacities, const float* d_weights,
                      float* d_raw_density, float* d_rgb, int64_t R, int P, int C, void* stream);
 
@@ -136,7 +141,8 @@ int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_density, const fl
  * inverse-CDF samples, concatenation with the input depths and ascending sort, one launch.
  *   lengths [R,P], weights [R,P] (raymarcher weights; the kernel uses weights[:,1:-1])
  *   u: the draws, row stride u_row_stride floats: n_new (or more) for per-ray torch.rand draws, 0 for one
- *      shared row (the deterministic linspace(0,1,n_new) of renderers/utils.py:130-132)
+ *      shared row (the deterministic linspace(0,1,n_new) of renderers/utils.py:130-132); NULL with rng_state != NULL:
+ *      per-ray U[0,1) draws generated in the kernel (no [R,n_new] tensor in HBM)
  *   out: new_lengths [R, n_new + (add_input_samples ? P : 0)] sorted ascending
  *        inds [R,n_new] int64 searchsorted indices (may be NULL)
  *        flag[0] (int32, device) is set to 1 if any weight + eps <= 0 (reference raises ValueError,
@@ -145,13 +151,56 @@ int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_density, const fl
  * sum rounded per prefix) so indices are bit-identical to the reference's --device cpu path.
  * ---------------------------------------------------------------------------------------------- */
 int yn_sample_pdf_merge(const float* lengths, const float* weights, const float* u, int64_t u_row_stride,
-                        float* new_lengths, int64_t* inds, int32_t* flag, int64_t R, int P, int n_new,
-                        int add_input_samples, void* stream);
+                        const int64_t* rng_state, int rng_site, float* new_lengths, int64_t* inds, int32_t* flag,
+                        int64_t R, int P, int n_new, int add_input_samples, void* stream);
 
 /* Plain sample_pdf_python (renderers/utils.py:83-158) on explicit bin edges: bins [R,n_bins],
  * weights [R,n_bins-1] -> samples [R,n_samples] in draw order (not sorted), same rounding contract. */
 int yn_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_row_stride, float* samples,
                   int64_t* inds, int32_t* flag, int64_t R, int n_bins, int n_samples, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * In-kernel draws of the training step.  rng_state: int64[4] in DEVICE memory = {seed, steps begun,
+ * current step (snapshot), reserved}.  Philox4x32-10, key = seed (+ step high word), counter = (row, group of four
+ * consecutive elements, draw site, step): uniforms carry 24 random bits like torch.rand, normals are Box-Muller pairs.
+ * Reference draw sites: stratified jitter rand_like (ray_sampler.py:384), density noise randn_like
+ * (multipass_emission_absorpsion_renderer.py:203-207), inverse-CDF uniforms torch.rand (renderers/utils.py:133-134).
+ * An explicit draw pointer always takes precedence (parity tests replay the reference's draws through it).
+ * ---------------------------------------------------------------------------------------------- */
+/* One thread: rng_state[2] = rng_state[1]++ (the snapshot every kernel of the step keys its draws with) and
+ * adam_state[0] += 1 (the float step counter yn_adam_step_dev reads).  Either pointer may be NULL. */
+int yn_step_begin(int64_t* rng_state, float* adam_state, void* stream);
+
+/* Training rays in ONE launch: the unmasked pixel pick of yn_sample_pixels (keyed by rng_state), the pinhole rays of
+ * yn_ray_bundle and the stratified depths with the jitter drawn in the kernel (site rng_site) when stratified != 0.
+ *   out: idx_out int64 [B,n] (may be NULL), xy_out [B,n,2], origins / directions [B,n,3], lengths [B,n,P] */
+int yn_train_rays(const int64_t* rng_state, int rng_site, const float* poses, int64_t pose_batch_stride,
+                  int64_t pose_row_stride, const float* focal, const float* depths, int stratified, int64_t* idx_out,
+                  float* xy_out, float* origins, float* directions, float* lengths, int64_t B, int64_t n, int P,
+                  int width, int height, void* stream);
+
+/* The draws the kernels generate for (rng_site, current step), written out: out [R,P]; kind 0 = U[0,1), 1 = N(0,1).
+ * Feeding them back through the explicit draw pointers reproduces the in-kernel path bit for bit (tests). */
+int yn_rng_fill(const int64_t* rng_state, int rng_site, int kind, float* out, int64_t R, int P, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-image rgb losses: ground-truth gather at the sampled pixels (sample_grid, pipelines/utils.py:272-296:
+ * flat index = (x + width * y).long()) fused with _rgb_metrics (137-158): mse[b] = mean over (rays x channels) of
+ * (pred - gt)^2 and huber[b] = (sqrt(max(1 + mse / 0.03^2, 0) + 1e-4) - 1) * 0.03 (189-203).
+ *   pred [B,n,C], image [B,height,width,C], xy [B,n,2] -> mse [B], huber [B]; deterministic reduction order.
+ * Backward: d_pred [B,n,C] for incoming g_mse [B], g_huber [B] (either may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int yn_rgb_loss_fwd(const float* pred, const float* image, const float* xy, float* mse, float* huber, int64_t B,
+                    int64_t n, int C, int width, int height, void* stream);
+int yn_rgb_loss_bwd(const float* pred, const float* image, const float* xy, const float* mse, const float* g_mse,
+                    const float* g_huber, float* d_pred, int64_t B, int64_t n, int C, int width, int height,
+                    void* stream);
+
+/* scatter_rays_to_image (pipelines/utils.py:299-323) for up to three tensors at once: src[k] [B,n,channels[k]] is
+ * written to the CALLER-ZEROED canvas dst[k] [B,height,width,channels[k]] at flat pixel (x + width * y).long().
+ * src / dst / channels are HOST arrays of n_tensors entries. */
+int yn_scatter_rays(const float* const* src, float* const* dst, const int* channels, int n_tensors, const float* xy,
+                    int64_t B, int64_t n, int width, int height, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * torch.optim.Adam step (scripts/run.py:159; weight_decay 0, amsgrad off) on flat buffers; grad_scale

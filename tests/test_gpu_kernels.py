@@ -424,8 +424,9 @@ def test_refiner_fast_and_generic_kernels_agree_bitwise(P, n):
         inds_g = torch.empty(R, n, dtype=torch.int64, device=DEV)
         flag = torch.zeros(1, dtype=torch.int32, device=DEV)
         uarg, stride = (ops.det_draws(n, zt.device), 0) if uu is None else (uu, n)
-        ops._call("yn_sample_pdf_merge", ops.N.ptr(zt), ops.N.ptr(wt), ops.N.ptr(uarg), stride,
-                  ctypes_ptr(out), ops.N.ptr(inds_g, torch.int64), ops.N.ptr(flag, torch.int32), R, P, n, 1, ops.N.stream_ptr())
+        ops._call("yn_sample_pdf_merge", ops.N.ptr(zt), ops.N.ptr(wt), ops.N.ptr(uarg), stride, None, 0,
+                  ctypes_ptr(out), ops.N.ptr(inds_g, torch.int64), ops.N.ptr(flag, torch.int32), R, P, n, 1, ops.STREAM,
+                  device=zt.device)
         same(inds_f, inds_g.cpu(), "inds")
         same(fast, out.cpu(), "lengths")
         ref, ref_inds = O.refine_lengths(T(z), T(w), n, None if uu is None else T(u))
@@ -516,3 +517,96 @@ def test_adam_kernel_vs_torch_and_oracle(world):
             # one ulp of the parameter itself (|p| ~ 1) is the floor of every single update
             close(p_ - p0.to(DEV), pr - p0, 1e-5, 10 * ulp * (float(p0.abs().max()) + 5e-3), f"{name} parameter update vs {ref_name}")
     assert torch.equal(pk, pd) or float((pk - pd).abs().max()) <= 1e-9
+
+
+# --------------------------------------------------------------------------- in-kernel draws
+def test_device_rng_matches_explicit_draws_bitwise():
+    """Every randomised kernel has two draw sources: an explicit tensor (the parity tests replay the reference's draws
+    through it) and the in-kernel Philox stream.  `yn_rng_fill` writes out the stream; feeding it back through the
+    explicit pointers must give the same bits as the in-kernel path: stratified depths, density noise forward AND backward
+    (blocked and generic kernels), inverse-CDF uniforms (fast and generic kernels)."""
+    from yanerf import ops
+
+    rng = ops.DeviceRng(DEV, seed=1234)
+    ops.step_begin(rng, None)
+    ops.step_begin(rng, None)  # current step = 1
+    rs = np.random.RandomState(3)
+    # --- stratified jitter + pixel pick
+    B, n, P, H, W = 2, 300, 64, 40, 50
+    poses, focal = syn.synth_camera(B, seed=1).to(DEV), torch.full((B,), 33.0, device=DEV)
+    depths = O.depth_linspace(2.0, 6.0, P).to(DEV)
+    idx, xys, o, d, z = ops.train_rays(rng, poses, focal, depths, True, n, W, H)
+    for b in range(B):
+        assert idx[b].unique().numel() == n and int(idx[b].min()) >= 0 and int(idx[b].max()) < H * W
+    assert torch.equal(xys[..., 0].long() + W * xys[..., 1].long(), idx)
+    u = ops.rng_fill(rng, ops.DeviceRng.SITE_STRATIFIED, B * n, P, normal=False).reshape(B, n, P)
+    o2, d2, z2, _ = ops.ray_bundle(poses, focal, xys, depths, u, n, W, H)
+    same(z, z2.cpu(), "stratified depths"); same(o, o2.cpu(), "origins"); same(d, d2.cpu(), "directions")
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0 and abs(float(u.mean()) - 0.5) < 0.01
+    assert abs(float(u.var()) - 1 / 12) < 0.005
+    # --- density noise: in-kernel vs explicit, forward and backward, P = 64 / 192 (blocked) and 37 (generic)
+    for Pn in (64, 192, 37):
+        R = 500
+        sig = T((rs.standard_normal(size=(R, Pn)) * 0.5).astype(np.float32)).to(DEV)
+        rgb = T(rs.uniform(size=(R, Pn, 3)).astype(np.float32)).to(DEV)
+        zz = T(np.sort(2 + 4 * rs.uniform(size=(R, Pn)), axis=-1).astype(np.float32)).to(DEV)
+        dd = T(rs.standard_normal(size=(R, 3)).astype(np.float32)).to(DEV)
+        cfg = ops.march_cfg(1e10, 1e-6, 0.3, False, False, (0.0, 0.0, 0.0))
+        site = ops.DeviceRng.SITE_NOISE + 1
+        noise = ops.rng_fill(rng, site, R, Pn, normal=True)
+        outs = []
+        for kw in (dict(noise=noise), dict(rng=rng, site=site)):
+            a, b_ = sig.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
+            f, dep, op, w = ops.composite(a, b_, zz, dd, cfg, **kw)
+            (f.sum() + (w * w).sum()).backward()
+            outs.append((f, dep, w, a.grad, b_.grad))
+        for x, y, name in zip(outs[0], outs[1], ("features", "depths", "weights", "d_sigma", "d_rgb")):
+            same(y, x.detach().cpu(), f"P={Pn} {name}")
+        assert abs(float(noise.mean())) < 0.02 and abs(float(noise.var()) - 1.0) < 0.03
+        assert abs(float((noise ** 4).mean()) - 3.0) < 0.3  # kurtosis of a normal
+    # --- inverse-CDF uniforms: fast kernel (64 -> +128) and generic kernel (50 -> +20)
+    for Pn, nn in ((64, 128), (50, 20)):
+        R = 700
+        zz = T(np.sort(2 + 4 * rs.uniform(size=(R, Pn)), axis=-1).astype(np.float32)).to(DEV)
+        ww = T((rs.uniform(size=(R, Pn)) ** 4).astype(np.float32)).to(DEV)
+        site = ops.DeviceRng.SITE_PDF
+        uu = ops.rng_fill(rng, site, R, nn, normal=False)
+        a, ia, _ = ops.sample_pdf_merge(zz, ww, nn, uu, want_inds=True)
+        b_, ib, _ = ops.sample_pdf_merge(zz, ww, nn, None, want_inds=True, rng=rng, site=site)
+        same(b_, a.cpu(), f"refined depths P={Pn}"); same(ib, ia.cpu(), f"inds P={Pn}")
+        ref, ref_inds = O.refine_lengths(zz.cpu(), ww.cpu(), nn, uu.cpu())
+        same(b_, ref, "in-kernel draws vs oracle on the same uniforms"); same(ib, ref_inds, "inds vs oracle")
+    # --- a new step gives new draws; the same step gives the same draws
+    u_again = ops.rng_fill(rng, ops.DeviceRng.SITE_STRATIFIED, B * n, P, normal=False).reshape(B, n, P)
+    assert torch.equal(u, u_again)
+    ops.step_begin(rng, None)
+    u_next = ops.rng_fill(rng, ops.DeviceRng.SITE_STRATIFIED, B * n, P, normal=False).reshape(B, n, P)
+    assert not torch.equal(u, u_next) and abs(float((u * u_next).mean()) - 0.25) < 0.01  # uncorrelated
+
+
+def test_rgb_loss_and_scatter_kernels_vs_torch():
+    """`yn_rgb_loss_fwd/bwd` (GT gather + per-image mse / huber) and `yn_scatter_rays` against the torch ops they replace
+    (the reference's sample_grid / _rgb_metrics / scatter_rays_to_image, pipelines/utils.py)."""
+    from yanerf import ops
+    from yanerf.pipelines.utils import _rgb_metrics, sample_grid, scatter_rays_to_image
+
+    B, H, W, n = 3, 30, 44, 1000
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand(B, H, W, 3, generator=g).to(DEV)
+    idx = torch.stack([torch.randperm(H * W, generator=g)[:n] for _ in range(B)]).to(DEV)
+    xy = torch.stack((idx % W, idx // W), dim=-1).float()
+    pred = torch.rand(B, n, 3, generator=g).to(DEV)
+    p1 = pred.clone().requires_grad_(True)
+    ref = _rgb_metrics(sample_grid(image, xy[:, :, None], validate=False), p1[:, :, None])
+    (ref["rgb_mse"] * torch.tensor([1.0, 2.0, 3.0], device=DEV)).sum().add(ref["rgb_huber"].sum() * 0.5).backward()
+    p2 = pred.clone().requires_grad_(True)
+    mse, hub = ops.rgb_loss(p2, image, xy)
+    (mse * torch.tensor([1.0, 2.0, 3.0], device=DEV)).sum().add(hub.sum() * 0.5).backward()
+    close(mse, ref["rgb_mse"].detach().cpu(), 1e-6, 0, "mse")
+    close(hub, ref["rgb_huber"].detach().cpu(), 1e-5, 1e-9, "huber")
+    close(p2.grad, p1.grad.cpu(), 1e-5, 1e-10, "d_pred")
+    dep, alp = torch.rand(B, n, 1, device=DEV), torch.rand(B, n, 1, device=DEV)
+    outs = ops.scatter_rays([pred, dep, alp], xy, H, W)
+    for got, src in zip(outs, (pred, dep, alp)):
+        assert got.is_contiguous()
+        same(got, scatter_rays_to_image(src[:, :, None], xy[:, :, None], H, W).cpu(), "scatter")

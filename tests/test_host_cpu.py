@@ -56,11 +56,11 @@ def test_size_queries_and_validation_without_gpu():
         N.check(rc)
     cfg = N.MarchCfg()
     cfg.bg_channels = 2
-    rc = lib.yn_composite_fwd(ctypes.byref(cfg), *([None] * 10), 4, 8, 3, None)
+    rc = lib.yn_composite_fwd(ctypes.byref(cfg), *([None] * 6), 0, *([None] * 5), 4, 8, 3, None)
     assert rc == -1 and b"Wrong number of background color channels" in lib.yn_last_error_string()
     with pytest.raises(ValueError):
         N.check(rc)
-    assert lib.yn_sample_pdf_merge(None, None, None, 0, None, None, None, 4, 2, 8, 1, None) == -1  # P < 3
+    assert lib.yn_sample_pdf_merge(None, None, None, 0, None, 0, None, None, None, 4, 2, 8, 1, None) == -1  # P < 3
     assert lib.yn_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -1  # step < 1
 
 

@@ -89,6 +89,7 @@ int main(int argc, char** argv) {
   const int n_blocks = argc > 1 ? atoi(argv[1]) : 40000;  // 16 KB blocks per CTA and stream
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int n_ctas = argc > 2 ? atoi(argv[2]) : sms;  // fewer CTAs than SMs: is the cap per SM or chip-wide?
   const size_t big = (size_t)8 << 30;
   uint8_t *d_a, *d_b, *d_ring;
   cudaMalloc(&d_a, big);
@@ -118,7 +119,6 @@ int main(int argc, char** argv) {
       {"read own + write own (all L2)", {own(0), own(0), none}},
       {"read hbm + write own ring + read nbr ring", {hbm(d_a, 0), own(0), nbr(0)}},
       {"read hbm + write own ring + read nbr ring, hints", {hbm(d_a, 2), own(1), nbr(1)}},
-      {"read hbm + write hbm + read hbm (today's backward)", {hbm(d_a, 0), hbm(d_b, 0), hbm(d_a + slice / 2 / kBlk * kBlk, 0)}},
   };
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -127,7 +127,7 @@ int main(int argc, char** argv) {
     float best = 1e30f;
     for (int it = 0; it < 3; ++it) {
       cudaEventRecord(e0);
-      bw_kernel<<<sms, 96, smem>>>(c.p);
+      bw_kernel<<<n_ctas, 96, smem>>>(c.p);
       cudaEventRecord(e1);
       cudaError_t err = cudaDeviceSynchronize();
       if (err != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(err)); return 1; }
@@ -135,8 +135,8 @@ int main(int argc, char** argv) {
       cudaEventElapsedTime(&ms, e0, e1);
       if (ms < best) best = ms;
     }
-    const double per = (double)n_blocks * kBlk * sms / best / 1e9;
-    printf("{\"case\": \"%s\", \"ms\": %.3f, \"r1_TBps\": %.2f, \"w_TBps\": %.2f, \"r2_TBps\": %.2f, \"total_TBps\": %.2f}\n", c.name, best,
+    const double per = (double)n_blocks * kBlk * n_ctas / best / 1e9;
+    printf("{\"ctas\": %d, \"case\": \"%s\", \"ms\": %.3f, \"r1_TBps\": %.2f, \"w_TBps\": %.2f, \"r2_TBps\": %.2f, \"total_TBps\": %.2f}\n", n_ctas, c.name, best,
            c.p.r1.n ? per : 0.0, c.p.w.n ? per : 0.0, c.p.r2.n ? per : 0.0, per * ((c.p.r1.n > 0) + (c.p.w.n > 0) + (c.p.r2.n > 0)));
   }
   return 0;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "mlp_common.cuh"
+#include "rng.cuh"
 
 namespace ynb {
 
@@ -21,6 +22,7 @@ struct MarchParams {
   const float* z;
   const float* dirs;
   const float* noise;
+  RngRef rng;  // in-kernel N(0,1) density noise when `noise` is null (training, density_noise_std > 0)
   const float* bg;
   float* features;
   float* depths;
@@ -71,7 +73,10 @@ __device__ __forceinline__ SampleState march_chunk(const MarchParams& p, int64_t
   if (valid) {
     zi = __ldg(p.z + base + i);
     sr = __ldg(p.sigma + base + i);
-    if (p.noise != nullptr && p.cfg.density_noise_std > 0.f) sr = sr + __ldg(p.noise + base + i) * p.cfg.density_noise_std;
+    if (p.cfg.density_noise_std > 0.f) {
+      if (p.noise != nullptr) sr = sr + __ldg(p.noise + base + i) * p.cfg.density_noise_std;
+      else if (p.rng.state != nullptr) sr = sr + NormalRow(p.rng, base / p.P).get(i) * p.cfg.density_noise_std;
+    }
     if (i + 1 < p.P) zn = __ldg(p.z + base + i + 1);
   }
   float delta = (i == p.P - 1) ? p.cfg.background_opacity : (zn - zi);
@@ -260,7 +265,8 @@ static int validate(const char* name, const yn_march_cfg* cfg, int64_t R, int P,
 }  // namespace ynb
 
 extern "C" int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_density, const float* rgb,
-                                const float* lengths, const float* directions, const float* noise, const float* bg,
+                                const float* lengths, const float* directions, const float* noise,
+                                const int64_t* rng_state, int rng_site, const float* bg,
                                 float* features, float* depths, float* opacities, float* weights, int64_t R, int P,
                                 int C, void* stream) {
   if (int rc = ynb::validate("yn_composite_fwd", cfg, R, P, C)) return rc;
@@ -270,6 +276,7 @@ extern "C" int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_densit
   ynb::MarchParams p = {};
   p.cfg = *cfg;
   p.sigma = raw_density; p.rgb = rgb; p.z = lengths; p.dirs = directions; p.noise = noise; p.bg = bg;
+  p.rng.state = rng_state; p.rng.site = rng_site;
   p.features = features; p.depths = depths; p.opacities = opacities; p.weights = weights;
   p.R = R; p.P = P; p.C = C;
   const int wpb = 8;
@@ -285,7 +292,8 @@ extern "C" int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_densit
 }
 
 extern "C" int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_density, const float* rgb,
-                                const float* lengths, const float* directions, const float* noise, const float* bg,
+                                const float* lengths, const float* directions, const float* noise,
+                                const int64_t* rng_state, int rng_site, const float* bg,
                                 const float* d_features, const float* d_depths, const float* d_opacities,
                                 const float* d_weights, float* d_raw_density, float* d_rgb, int64_t R, int P, int C,
                                 void* stream) {
@@ -296,6 +304,7 @@ extern "C" int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_densit
   ynb::MarchParams p = {};
   p.cfg = *cfg;
   p.sigma = raw_density; p.rgb = rgb; p.z = lengths; p.dirs = directions; p.noise = noise; p.bg = bg;
+  p.rng.state = rng_state; p.rng.site = rng_site;
   p.d_features = d_features; p.d_depths = d_depths; p.d_opacities = d_opacities; p.d_weights = d_weights;
   p.d_sigma = d_raw_density; p.d_rgb = d_rgb;
   p.R = R; p.P = P; p.C = C;

@@ -51,9 +51,15 @@ __device__ __forceinline__ void march_blocked(const MarchParams& p, int64_t base
   const int s0 = lane * S;
   load_row<S>(p.z + base + s0, s.z);
   load_row<S>(p.sigma + base + s0, s.sr);
-  if (p.noise != nullptr && p.cfg.density_noise_std > 0.f) {
+  if (p.cfg.density_noise_std > 0.f && (p.noise != nullptr || p.rng.state != nullptr)) {
     float nz[S];
-    load_row<S>(p.noise + base + s0, nz);
+    if (p.noise != nullptr) {
+      load_row<S>(p.noise + base + s0, nz);
+    } else {  // in-kernel draws: the same (ray, sample) -> value map in the forward and the backward kernel
+      NormalRow gen(p.rng, base / (32 * S));
+#pragma unroll
+      for (int k = 0; k < S; ++k) nz[k] = gen.get(s0 + k);
+    }
 #pragma unroll
     for (int k = 0; k < S; ++k) s.sr[k] = s.sr[k] + nz[k] * p.cfg.density_noise_std;
   }

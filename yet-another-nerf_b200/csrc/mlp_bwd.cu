@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       const int64_t rtile = tile_live ? tile : 0;
       // this row's ReLU sign masks (32 B per layer): mask m at A.mask_offset(m)
       const uint8_t* mask_rows = p.stash + (size_t)rtile * blocks_per_tile * kBlkBytes + (size_t)row * 32;
-      uint8_t* gstash_tile = p.gstash + (size_t)rtile * blocks_per_tile * kBlkBytes;
+      // (YN_BWD_DEBUG bit 32, timing experiment: every gradient-stash store lands in a 64-tile window that stays in L2)
+      uint8_t* gstash_tile = p.gstash + (size_t)((p.debug & 32) ? rtile % 64 : rtile) * blocks_per_tile * kBlkBytes;
 
       if (leader) bulk_wait_read<0>();
       bwd_named_bar_sync(1 + g, 128);
@@ -421,8 +422,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
       for (int64_t t = split; t < n_tiles; t += n_splits) {
-        const uint8_t* st = p.stash + (size_t)t * blocks_per_tile * kBlkBytes;
-        const uint8_t* gs = p.gstash + (size_t)t * blocks_per_tile * kBlkBytes;
+        // (YN_BWD_DEBUG bit 64, timing experiment: operands come from a 64-tile window that stays in L2)
+        const int64_t ts = (p.debug & 64) ? t % 64 : t;
+        const uint8_t* st = p.stash + (size_t)ts * blocks_per_tile * kBlkBytes;
+        const uint8_t* gs = p.gstash + (size_t)ts * blocks_per_tile * kBlkBytes;
         const uint32_t dst = smem_base + slot * kWgStageBytes;
         const uint32_t bar = bar_full + 8 * slot;
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);

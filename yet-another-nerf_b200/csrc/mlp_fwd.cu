@@ -49,7 +49,7 @@ struct FwdParams {
   int64_t n_points;
   int P;
   long long* trace;  // timing experiments only (YN_FWD_TRACE=<file>): CTA 0 logs (tag, clock64) pairs, 4 roles x 2048 events
-  int debug;  // timing experiments only (YN_FWD_DEBUG bit mask): 1 = epilogue skips TMEM/STS work, 2 = producer skips the copies
+  int debug;  // timing experiments only (YN_FWD_DEBUG bit mask): 1 = epilogue skips TMEM/STS work, 2 = producer skips the copies, 4 = stash into an L2-resident window
 };
 
 constexpr int kTraceEvents = 2048;
@@ -486,7 +486,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       const int64_t gidx = tile * kTileM + row;
       const bool valid = gidx < p.n_points;
       const int64_t ray = valid ? gidx / p.P : 0;
-      uint8_t* stash_tile = kStash ? p.stash + (size_t)tile * blocks_per_tile * kBlkBytes : nullptr;
+      // (YN_FWD_DEBUG bit 4, timing experiment: every stash store lands in a 64-tile window that stays in L2)
+      uint8_t* stash_tile = kStash ? p.stash + (size_t)((p.debug & 4) ? tile % 64 : tile) * blocks_per_tile * kBlkBytes : nullptr;
       const bool tile_live = tile < n_tiles;
 
       if (kStash) {

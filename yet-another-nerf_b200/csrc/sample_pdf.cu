@@ -19,13 +19,15 @@
 #include <math_constants.h>
 
 #include "mlp_common.cuh"
+#include "rng.cuh"
 
 namespace ynb {
 
 struct PdfParams {
   const float* z;
   const float* w;
-  const float* u;
+  const float* u;    // nullptr: U[0,1) draws generated in the kernel from `rng`
+  RngRef rng;
   int64_t u_stride;  // 0: one shared row of draws (deterministic linspace), n_new: per-ray draws
   float* out;
   int64_t* inds;
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p
     if (i >= 1 && i <= K) {
       const float wv = __fadd_rn(__ldg(wr + i), 1e-5f);
       s_cdf[i] = wv;  // wp[k] lives at s_cdf[k + 1]
-      bad |= !(wv > 0.f);
+      bad |= wv <= 0.f;  // like `weights.min() <= 0` (a NaN weight does not raise in the reference either)
     }
   }
   unsorted = __any_sync(0xffffffffu, unsorted);
@@ -259,9 +261,9 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p
   }
 
   // ---- inverse-CDF samples
-  const float* ur = p.u + ray * p.u_stride;
+  const float* ur = p.u ? p.u + ray * p.u_stride : nullptr;
   for (int j = lane; j < N; j += 32) {
-    const float u = __ldg(ur + j);
+    const float u = ur ? __ldg(ur + j) : UniformRow(p.rng, ray).get(j);
     int lo = 0, hi = NB;  // first index with cdf[idx] > u
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -352,17 +354,18 @@ static void launch_fast(const ynb::PdfParams& p, cudaStream_t st) {
 }
 
 static int launch_pdf(const float* lengths, const float* weights, const float* u, int64_t u_row_stride,
-                      float* new_lengths, int64_t* inds, int32_t* flag, int64_t R, int P, int n_new,
+                      const int64_t* rng_state, int rng_site, float* new_lengths, int64_t* inds, int32_t* flag, int64_t R, int P, int n_new,
                       int add_input_samples, int bins_mode, int sort_out, void* stream) {
   if (R < 0 || P < 3 || n_new < 1)
     return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_sample_pdf_merge: bad sizes R=%lld P=%d n_new=%d", (long long)R, P, n_new);
   if (R == 0) return YN_OK;
-  if (!lengths || !weights || !u || !new_lengths || !flag)
+  if (!lengths || !weights || (!u && !rng_state) || !new_lengths || !flag)
     return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_sample_pdf_merge: null pointer");
-  if (u_row_stride != 0 && u_row_stride < n_new)
+  if (u && u_row_stride != 0 && u_row_stride < n_new)
     return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_sample_pdf_merge: u_row_stride must be 0 or >= n_new");
   ynb::PdfParams p;
-  p.z = lengths; p.w = weights; p.u = u; p.u_stride = u_row_stride; p.out = new_lengths; p.inds = inds; p.flag = flag;
+  p.z = lengths; p.w = weights; p.u = u; p.u_stride = u ? u_row_stride : 0; p.out = new_lengths; p.inds = inds; p.flag = flag;
+  p.rng.state = rng_state; p.rng.site = rng_site;
   p.R = R; p.P = P; p.n_new = n_new; p.add_input = add_input_samples;
   int n2 = 1;
   while (n2 < P + n_new) n2 <<= 1;
@@ -372,7 +375,7 @@ static int launch_pdf(const float* lengths, const float* weights, const float* u
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
   if (!bins_mode && add_input_samples && sort_out && al8(lengths) && al8(weights) && al8(u) && al8(new_lengths) &&
-      (u_row_stride % 2 == 0)) {
+      (p.u_stride % 2 == 0)) {
     const int key = P * 1000 + n_new;
     bool done = true;
     switch (key) {
@@ -399,14 +402,14 @@ static int launch_pdf(const float* lengths, const float* weights, const float* u
 }
 
 extern "C" int yn_sample_pdf_merge(const float* lengths, const float* weights, const float* u, int64_t u_row_stride,
-                                   float* new_lengths, int64_t* inds, int32_t* flag, int64_t R, int P, int n_new,
-                                   int add_input_samples, void* stream) {
-  return launch_pdf(lengths, weights, u, u_row_stride, new_lengths, inds, flag, R, P, n_new, add_input_samples, 0, 1,
-                    stream);
+                                   const int64_t* rng_state, int rng_site, float* new_lengths, int64_t* inds,
+                                   int32_t* flag, int64_t R, int P, int n_new, int add_input_samples, void* stream) {
+  return launch_pdf(lengths, weights, u, u_row_stride, rng_state, rng_site, new_lengths, inds, flag, R, P, n_new,
+                    add_input_samples, 0, 1, stream);
 }
 
 extern "C" int yn_sample_pdf(const float* bins, const float* weights, const float* u, int64_t u_row_stride,
                              float* samples, int64_t* inds, int32_t* flag, int64_t R, int n_bins, int n_samples,
                              void* stream) {
-  return launch_pdf(bins, weights, u, u_row_stride, samples, inds, flag, R, n_bins, n_samples, 0, 1, 0, stream);
+  return launch_pdf(bins, weights, u, u_row_stride, nullptr, 0, samples, inds, flag, R, n_bins, n_samples, 0, 1, 0, stream);
 }

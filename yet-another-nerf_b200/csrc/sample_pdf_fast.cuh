@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_fast_kernel(const PdfPar
     if (i >= 1 && i <= K) {
       const float wv = __fadd_rn(wl[r], 1e-5f);
       s_cdf[i] = wv;  // wp[k] lives at s_cdf[k + 1]
-      bad |= !(wv > 0.f);
+      bad |= wv <= 0.f;
     }
   }
   unsorted = __any_sync(0xffffffffu, unsorted);
@@ -144,12 +144,18 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_fast_kernel(const PdfPar
   }
 
   // ---- inverse-CDF samples; lane i owns draws NPL*i .. NPL*i + NPL - 1
-  const float* ur = p.u + ray * p.u_stride + lane * NPL;
   float ul[NPL], v[NPL];
+  if (p.u != nullptr) {
+    const float* ur = p.u + ray * p.u_stride + lane * NPL;
 #pragma unroll
-  for (int k = 0; k < NPL / 2; ++k) {
-    const float2 a = __ldg(reinterpret_cast<const float2*>(ur) + k);
-    ul[2 * k] = a.x; ul[2 * k + 1] = a.y;
+    for (int k = 0; k < NPL / 2; ++k) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(ur) + k);
+      ul[2 * k] = a.x; ul[2 * k + 1] = a.y;
+    }
+  } else {  // in-kernel draws (training): no [R, N] tensor of uniforms in HBM
+    UniformRow gen(p.rng, ray);
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) ul[r] = gen.get(lane * NPL + r);
   }
 #pragma unroll
   for (int r = 0; r < NPL; ++r) {

@@ -65,9 +65,15 @@ SYMBOLS = {
     "yn_mlp_fwd": (c_int, [POINTER(MlpArch), _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "yn_mlp_bwd_workspace_bytes": (c_int64, [POINTER(MlpArch), c_int64]),
     "yn_mlp_bwd": (c_int, [POINTER(MlpArch), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
-    "yn_composite_fwd": (c_int, [POINTER(MarchCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
-    "yn_composite_bwd": (c_int, [POINTER(MarchCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
-    "yn_sample_pdf_merge": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "yn_composite_fwd": (c_int, [POINTER(MarchCfg), _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "yn_composite_bwd": (c_int, [POINTER(MarchCfg), _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "yn_sample_pdf_merge": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "yn_step_begin": (c_int, [_P, _P, _P]),
+    "yn_train_rays": (c_int, [_P, c_int, _P, c_int64, c_int64, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "yn_rgb_loss_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "yn_rng_fill": (c_int, [_P, c_int, c_int, _P, c_int64, c_int, _P]),
+    "yn_scatter_rays": (c_int, [_P, _P, _P, c_int, _P, c_int64, c_int64, c_int, c_int, _P]),
+    "yn_rgb_loss_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
     "yn_sample_pdf": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "yn_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_double, c_double, c_float, c_int32, c_float, _P]),
     "yn_adam_step_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, c_double, c_double, c_float, c_float, _P]),

@@ -115,6 +115,58 @@ def sample_pixels(seed: torch.Tensor, batch: int, n: int, width: int, height: in
     return idx, xy
 
 
+class DeviceRng:
+    """Device-resident generator state of the in-kernel draws (`int64[4]`: seed, steps begun, current step, reserved;
+    include/yanerf_b200.h "in-kernel draws").  `step_begin` snapshots the step; every kernel of the step keys its
+    Philox counters with (row, element group, site, step), so nothing random round-trips through HBM and a captured
+    CUDA graph advances by itself.  Sites: stratified jitter 0, density noise 16 + pass, inverse-CDF uniforms 32 + pass."""
+
+    SITE_STRATIFIED, SITE_NOISE, SITE_PDF = 0, 16, 32
+
+    def __init__(self, device, seed: Optional[int] = None) -> None:
+        if seed is None:  # from torch's CPU generator: reproducible under torch.manual_seed, no device sync
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
+        self.state = torch.tensor([seed, 0, 0, 0], dtype=torch.int64).to(device)
+
+    def seed(self, seed: int, step: int = 0) -> None:
+        self.state.copy_(torch.tensor([seed, step, max(step - 1, 0), 0], dtype=torch.int64))
+
+
+def rng_fill(rng: DeviceRng, site: int, rows: int, cols: int, normal: bool) -> torch.Tensor:
+    """The `[rows, cols]` draws the kernels generate for `site` in the current step (tests / debugging)."""
+    out = torch.empty(rows, cols, device=rng.state.device)
+    _call("yn_rng_fill", N.ptr(rng.state, torch.int64), site, int(bool(normal)), N.ptr(out), rows, cols, STREAM,
+          device=out.device)
+    return out
+
+
+def step_begin(rng: Optional[DeviceRng], adam_state: Optional[torch.Tensor]) -> None:
+    """One launch at the start of a training step: snapshot the step for the draws, bump Adam's device-side step."""
+    dev = rng.state.device if rng is not None else adam_state.device
+    _call("yn_step_begin", N.ptr(None if rng is None else rng.state, torch.int64), N.ptr(adam_state), STREAM, device=dev)
+
+
+def train_rays(rng: DeviceRng, poses: torch.Tensor, focal: torch.Tensor, depths: torch.Tensor, stratified: bool,
+               n_rays: int, width: int, height: int):
+    """Unmasked training pixel pick + `_xy_to_ray_bundle` + `_jiggle_within_stratas` in one launch
+    (ray_sampler.py:187-229, 249-314, 361-386), jitter drawn in the kernel.
+    Returns idx int64 [B,n], xys [B,n,2], origins [B,n,3], directions [B,n,3], lengths [B,n,P]."""
+    B, P, dev = poses.shape[0], depths.shape[0], poses.device
+    if poses.dtype != torch.float32 or poses.stride(2) != 1:
+        poses = poses.float().contiguous()
+    focal = N.f32c(focal.reshape(B))
+    depths = N.f32c(depths)
+    idx = torch.empty(B, n_rays, dtype=torch.int64, device=dev)
+    xys = torch.empty(B, n_rays, 2, device=dev)
+    origins = torch.empty(B, n_rays, 3, device=dev)
+    directions = torch.empty(B, n_rays, 3, device=dev)
+    lengths = torch.empty(B, n_rays, P, device=dev)
+    _call("yn_train_rays", N.ptr(rng.state, torch.int64), DeviceRng.SITE_STRATIFIED, ctypes.c_void_p(poses.data_ptr()),
+          poses.stride(0), poses.stride(1), N.ptr(focal), N.ptr(depths), int(bool(stratified)), N.ptr(idx, torch.int64),
+          N.ptr(xys), N.ptr(origins), N.ptr(directions), N.ptr(lengths), B, n_rays, P, width, height, STREAM, device=dev)
+    return idx, xys, origins, directions, lengths
+
+
 # --------------------------------------------------------------------------- #
 # NeRF MLP
 # --------------------------------------------------------------------------- #
@@ -235,7 +287,7 @@ class CompositeFunction(torch.autograd.Function):
     """EmissionAbsorptionRaymarcher.forward with its analytic backward."""
 
     @staticmethod
-    def forward(ctx, raw_density, rgb, lengths, directions, noise, bg, cfg: N.MarchCfg):
+    def forward(ctx, raw_density, rgb, lengths, directions, noise, bg, cfg: N.MarchCfg, rng=None, site: int = 0):
         R, P = lengths.shape
         C = rgb.shape[-1]
         dev = lengths.device
@@ -249,10 +301,13 @@ class CompositeFunction(torch.autograd.Function):
         depths = torch.empty(R, 1, device=dev)
         opacities = torch.empty(R, 1, device=dev)
         weights = torch.empty(R, P, device=dev)
+        rng_state = None if (rng is None or noise is not None) else rng.state
         _call("yn_composite_fwd",
               ctypes.byref(cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
+              N.ptr(rng_state, torch.int64), site,
               N.ptr(bg), N.ptr(features), N.ptr(depths), N.ptr(opacities), N.ptr(weights), R, P, C, STREAM, device=dev)
         ctx.cfg = cfg
+        ctx.rng = (rng_state, site)
         ctx.has = (noise is not None, bg is not None)
         saved = [raw_density, rgb, lengths, directions] + ([noise] if noise is not None else []) + ([bg] if bg is not None else [])
         ctx.save_for_backward(*saved)
@@ -276,9 +331,10 @@ class CompositeFunction(torch.autograd.Function):
                                                         for t in (d_features, d_depths, d_opacities, d_weights))
         _call("yn_composite_bwd",
               ctypes.byref(ctx.cfg), N.ptr(raw_density), N.ptr(rgb), N.ptr(lengths), N.ptr(directions), N.ptr(noise),
+              N.ptr(ctx.rng[0], torch.int64), ctx.rng[1],
               N.ptr(bg), N.ptr(d_features), N.ptr(d_depths), N.ptr(d_opacities),
               N.ptr(d_weights), N.ptr(d_sigma), N.ptr(d_rgb), R, P, C, STREAM, device=rgb.device)
-        return d_sigma, d_rgb, None, None, None, None, None
+        return d_sigma, d_rgb, None, None, None, None, None, None, None
 
 
 def _copy_cfg(cfg: N.MarchCfg) -> N.MarchCfg:
@@ -287,14 +343,16 @@ def _copy_cfg(cfg: N.MarchCfg) -> N.MarchCfg:
     return out
 
 
-def composite(raw_density, rgb, lengths, directions, cfg: N.MarchCfg, noise=None, bg=None):
+def composite(raw_density, rgb, lengths, directions, cfg: N.MarchCfg, noise=None, bg=None, rng: Optional[DeviceRng] = None,
+              site: int = 0):
     """raw_density [R,P], rgb [R,P,C], lengths [R,P], directions [R,3] -> features [R,C], depths [R,1],
-    opacities [R,1], weights [R,P]."""
+    opacities [R,1], weights [R,P].  Density noise (cfg.density_noise_std > 0): explicit `noise` [R,P], else drawn in the
+    kernel from `rng` (same values in the backward kernel as long as the step has not advanced)."""
     if raw_density.shape[0] == 0:
         R, P = lengths.shape
         z = lengths.new_zeros
         return z(R, rgb.shape[-1]), z(R, 1), z(R, 1), z(R, P)
-    return CompositeFunction.apply(raw_density, rgb, lengths, directions, noise, bg, cfg)
+    return CompositeFunction.apply(raw_density, rgb, lengths, directions, noise, bg, cfg, rng, site)
 
 
 # --------------------------------------------------------------------------- #
@@ -313,9 +371,11 @@ def det_draws(n: int, device) -> torch.Tensor:
 
 
 def sample_pdf_merge(lengths: torch.Tensor, weights: torch.Tensor, n_new: int, u: Optional[torch.Tensor],
-                     add_input_samples: bool = True, want_inds: bool = False, flag: Optional[torch.Tensor] = None):
+                     add_input_samples: bool = True, want_inds: bool = False, flag: Optional[torch.Tensor] = None,
+                     rng: Optional[DeviceRng] = None, site: int = 0):
     """lengths [R,P], weights [R,P] -> sorted new lengths [R, n_new (+P)], inds [R,n_new] int64 or None,
-    flag int32[1] (1 if any weight + 1e-5 <= 0)."""
+    flag int32[1] (1 if any weight + 1e-5 <= 0).  u: [R,n_new] draws; None = the deterministic linspace row, or, with
+    `rng`, per-ray uniforms drawn in the kernel."""
     R, P = lengths.shape
     dev = lengths.device
     out = torch.empty(R, n_new + (P if add_input_samples else 0), device=dev)
@@ -324,7 +384,10 @@ def sample_pdf_merge(lengths: torch.Tensor, weights: torch.Tensor, n_new: int, u
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
     if R == 0:
         return out, inds, flag
-    if u is None:
+    rng_state = None
+    if u is None and rng is not None:
+        rng_state, stride = rng.state, 0
+    elif u is None:
         u, stride = det_draws(n_new, dev), 0
     else:
         u = N.f32c(u)
@@ -332,8 +395,8 @@ def sample_pdf_merge(lengths: torch.Tensor, weights: torch.Tensor, n_new: int, u
         stride = n_new
     lengths, weights = N.f32c(lengths), N.f32c(weights)
     _call("yn_sample_pdf_merge",
-          N.ptr(lengths), N.ptr(weights), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
-          N.ptr(flag, torch.int32), R, P, n_new, int(add_input_samples), STREAM, device=dev)
+          N.ptr(lengths), N.ptr(weights), N.ptr(u), stride, N.ptr(rng_state, torch.int64), site, N.ptr(out),
+          N.ptr(inds, torch.int64), N.ptr(flag, torch.int32), R, P, n_new, int(add_input_samples), STREAM, device=dev)
     return out, inds, flag
 
 
@@ -356,6 +419,63 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Opt
           N.ptr(bins), N.ptr(weights), N.ptr(u), stride, N.ptr(out), N.ptr(inds, torch.int64),
           N.ptr(flag, torch.int32), R, nb, n_samples, STREAM, device=dev)
     return out, inds, flag
+
+
+# --------------------------------------------------------------------------- #
+# per-image rgb losses (ground-truth gather + squared-error mean)
+# --------------------------------------------------------------------------- #
+class RgbLossFunction(torch.autograd.Function):
+    """`sample_grid` + `_rgb_metrics` (pipelines/utils.py:137-158, 272-296) as one launch each way."""
+
+    @staticmethod
+    def forward(ctx, pred, image, xy):
+        B, n, C = pred.shape
+        Hh, Ww = image.shape[1], image.shape[2]
+        pred, image, xy = N.f32c(pred), N.f32c(image), N.f32c(xy)
+        mse = torch.empty(B, device=pred.device)
+        huber = torch.empty(B, device=pred.device)
+        _call("yn_rgb_loss_fwd", N.ptr(pred), N.ptr(image), N.ptr(xy), N.ptr(mse), N.ptr(huber), B, n, C, Ww, Hh, STREAM,
+              device=pred.device)
+        ctx.save_for_backward(pred, image, xy, mse)
+        return mse, huber
+
+    @staticmethod
+    def backward(ctx, g_mse, g_huber):
+        pred, image, xy, mse = ctx.saved_tensors
+        B, n, C = pred.shape
+        g_mse = None if g_mse is None else N.f32c(g_mse)
+        g_huber = None if g_huber is None else N.f32c(g_huber)
+        d_pred = torch.empty_like(pred)
+        _call("yn_rgb_loss_bwd", N.ptr(pred), N.ptr(image), N.ptr(xy), N.ptr(mse), N.ptr(g_mse), N.ptr(g_huber), N.ptr(d_pred),
+              B, n, C, image.shape[2], image.shape[1], STREAM, device=pred.device)
+        return d_pred, None, None
+
+
+def rgb_loss(pred: torch.Tensor, image: torch.Tensor, xy: torch.Tensor):
+    """pred [B,n,C], image [B,H,W,C], xy [B,n,2] float pixel coordinates -> (mse [B], huber [B])."""
+    return RgbLossFunction.apply(pred, image, xy)
+
+
+def scatter_rays(tensors: Sequence[torch.Tensor], xy: torch.Tensor, height: int, width: int):
+    """`scatter_rays_to_image` (pipelines/utils.py:299-323) for up to three `[B,n,C_k]` tensors at once: ONE zero fill of
+    a shared allocation + ONE launch; returns contiguous canvases `[B,H,W,C_k]`."""
+    B, n = xy.shape[0], xy.shape[1]
+    dev = xy.device
+    srcs = [N.f32c(t.reshape(B, n, t.shape[-1])) for t in tensors]
+    chans = [t.shape[-1] for t in srcs]
+    buf = torch.zeros(B * height * width * sum(chans), device=dev)
+    outs, off = [], 0
+    for c in chans:
+        k = B * height * width * c
+        outs.append(buf[off:off + k].view(B, height, width, c))
+        off += k
+    xy = N.f32c(xy)
+    m = len(srcs)
+    src_arr = (ctypes.c_void_p * m)(*[t.data_ptr() for t in srcs])
+    dst_arr = (ctypes.c_void_p * m)(*[t.data_ptr() for t in outs])
+    ch_arr = (ctypes.c_int * m)(*chans)
+    _call("yn_scatter_rays", src_arr, dst_arr, ch_arr, m, N.ptr(xy), B, n, width, height, STREAM, device=dev)
+    return outs
 
 
 # --------------------------------------------------------------------------- #

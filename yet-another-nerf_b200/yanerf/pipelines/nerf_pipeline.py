@@ -164,6 +164,14 @@ class NeRFPipeline(torch.nn.Module):
         self.log_loss_weights()
         self.view_metrics = ViewMetrics()
 
+    def set_device_rng(self, rng) -> None:
+        """Hand an `ops.DeviceRng` to every draw site of the training forward (ray sampler, raymarcher, refiners): the
+        draws are then generated inside the consuming kernels.  None restores torch's generators (reference behaviour,
+        and what the parity tests' draw injection hooks into)."""
+        for m in (self.ray_sampler, self.renderer):
+            if hasattr(m, "set_device_rng"):
+                m.set_device_rng(rng)
+
     def log_loss_weights(self) -> None:
         rows = "\n".join(f"{k:40s}: {w:1.2e}" for k, w in self.loss_weights.items())
         self.logger.info("-------\nloss_weights:\n" + rows + "\n-------")
@@ -321,4 +329,13 @@ class NeRFPipeline(torch.nn.Module):
     def _rasterize_mc_samples(self, xys, bg_color, image_height, image_width, rendered_dict):
         if image_height is None or image_width is None:
             image_height, image_width = self.render_image_height, self.render_image_width
+        vals = list(rendered_dict.values())
+        if bg_color is None and xys.is_cuda and 1 <= len(vals) <= 3:
+            # one zero fill + one launch for rgb / depth / alpha together (`yn_scatter_rays`)
+            from yanerf import ops
+
+            with torch.no_grad():
+                B = xys.shape[0]
+                outs = ops.scatter_rays([v.detach() for v in vals], xys.reshape(B, -1, 2), image_height, image_width)
+            return dict(zip(rendered_dict.keys(), outs))
         return {k: scatter_rays_to_image(v, xys, image_height, image_width, bg_color) for k, v in rendered_dict.items()}

@@ -70,6 +70,9 @@ class _RaySampler(torch.nn.Module):
         # consumes torch's global generator here.  FusedTrainer turns it on.
         self.fused_pixel_sampler = False
         self._pixel_seed: Optional[torch.Tensor] = None
+        # ops.DeviceRng: with the fused pixel sampler, pick + rays + stratified jitter become ONE launch (`yn_train_rays`)
+        # whose draws are generated in the kernel; None = torch's generators (`torch.rand`), as in the reference
+        self.device_rng = None
 
     def forward(self, poses, focal_lengths, *, image_height=None, image_width=None, mask=None,
                 sampling_prob_mask=None, min_depth=None, max_depth=None,
@@ -117,6 +120,22 @@ class _RaySampler(torch.nn.Module):
                         f"Invalida `sampling_prob_mask`, shape of {sampling_prob_mask.shape}, want (B, H, W) or (B, L, H, W)"
                     )
             xy_fused = None
+            if fused and self.device_rng is not None:
+                md = self._min_depth if min_depth is None else min_depth
+                xd = self._max_depth if max_depth is None else max_depth
+                if isinstance(md, torch.Tensor):
+                    md = md.mean().item()
+                if isinstance(xd, torch.Tensor):
+                    xd = xd.mean().item()
+                n_pts = self._n_pts_per_ray if n_pts_per_ray is None else n_pts_per_ray
+                stratified = self._stratified_sampling if stratified_sampling is None else stratified_sampling
+                _, xys, o, d, z = ops.train_rays(self.device_rng, poses, focal_lengths, _depth_row(md, xd, n_pts, device),
+                                                 bool(stratified and n_pts > 0), num_rays, self._image_width,
+                                                 self._image_height) if (W, H) == (self._image_width, self._image_height) else (None,) * 5
+                if xys is not None:
+                    sp = (num_rays, 1)
+                    return RayBundle(origins=o.reshape(B, *sp, 3), directions=d.reshape(B, *sp, 3),
+                                     lengths=z.reshape(B, *sp, n_pts), xys=xys.reshape(B, *sp, 2))
             if fused:
                 if self._pixel_seed is None or self._pixel_seed.device != device:
                     # seeded from torch's CPU generator: reproducible under torch.manual_seed, no device sync
@@ -203,6 +222,11 @@ class RaySampler(torch.nn.Module):
     def fused_pixel_sampler(self, value: bool) -> None:
         for s in self._raysamplers.values():  # plain dict, not sub-modules: `.modules()` does not reach them
             s.fused_pixel_sampler = bool(value)
+
+    def set_device_rng(self, rng) -> None:
+        """In-kernel draws for the training sampler (ops.DeviceRng; None switches back to torch's generators)."""
+        for s in self._raysamplers.values():
+            s.device_rng = rng
 
     def forward(self, poses, focal_lengths, evaluation_mode: EvaluationMode, *, mask=None, sampling_prob_mask=None,
                 image_height=None, image_width=None, min_depth=None, max_depth=None,

@@ -64,9 +64,10 @@ class EmissionAbsorptionRaymarcher(torch.nn.Module):
             bg_color = torch.tensor(bg_color, dtype=torch.float32)
         self.register_buffer("_bg_color", bg_color, persistent=False)
         self._bg_host = [float(v) for v in bg_color.reshape(-1).tolist()]
+        self.device_rng = None  # ops.DeviceRng: density noise drawn in the kernel instead of torch.randn_like
 
     def forward(self, rays_densities, rays_features, aux: Dict[str, Any], ray_lengths, ray_directions,
-                density_noise_std: float = 0.0, bg_color: Optional[torch.Tensor] = None):
+                density_noise_std: float = 0.0, bg_color: Optional[torch.Tensor] = None, rng_pass: int = 0):
         """rays_densities `[...,P,1]`, rays_features `[...,P,C]`, ray_lengths `[...,P]`, ray_directions `[...,3]`
         -> features `[...,C]`, depths `[...,1]`, opacities `[...,1]`, weights `[...,P]`, aux."""
         _check_raymarcher_inputs(rays_densities, rays_features, ray_lengths, z_can_be_none=True,
@@ -81,11 +82,12 @@ class EmissionAbsorptionRaymarcher(torch.nn.Module):
         cfg = ops.march_cfg(self.background_opacity, self.background_density_bias, float(density_noise_std),
                             self.blend_output, self.hard_background, self._bg_host)
         sigma = rays_densities.reshape(-1, P)
-        noise = torch.randn_like(sigma) if density_noise_std > 0.0 else None
+        rng = self.device_rng if density_noise_std > 0.0 else None
+        noise = torch.randn_like(sigma) if (density_noise_std > 0.0 and rng is None) else None
         bg = None if bg_color is None else bg_color.expand(*lead, n_bg).reshape(-1, n_bg)
         feats, depths, opac, weights = ops.composite(
             sigma, rays_features.reshape(-1, P, C), ray_lengths.reshape(-1, P),
-            ray_directions.expand(*lead, 3).reshape(-1, 3), cfg, noise, bg,
+            ray_directions.expand(*lead, 3).reshape(-1, 3), cfg, noise, bg, rng, ops.DeviceRng.SITE_NOISE + rng_pass,
         )
         return (feats.reshape(*lead, C), depths.reshape(*lead, 1), opac.reshape(*lead, 1),
                 weights.reshape(*lead, P), aux)
@@ -122,16 +124,28 @@ class MultipassEmissionAbsorpsionRenderer(torch.nn.Module):
         return self._run_raymarcher(origins, directions, lengths, xys, bg_color, implicit_functions, None,
                                     evaluation_mode, **kwargs)
 
+    def set_device_rng(self, rng) -> None:
+        """In-kernel draws (ops.DeviceRng) for the density noise and the refiners' inverse-CDF uniforms; None switches
+        back to torch's generators."""
+        self._raymarcher.device_rng = rng
+        for r in self._refiners.values():
+            r.device_rng = rng
+
     def _run_raymarcher(self, origins, directions, lengths, xys, bg_color, implicit_functions, prev_stage,
                         evaluation_mode, **kwargs) -> RendererOutput:
         noise_std = self.density_noise_std_train if evaluation_mode == EvaluationMode.TRAINING else 0.0
+        pass_idx = 0
+        stage = prev_stage
+        while stage is not None:
+            pass_idx, stage = pass_idx + 1, stage.prev_stage
         features, depths, alpha_masks, weights, aux = self._raymarcher(
             **implicit_functions[0](origins, directions, lengths, **kwargs),
             ray_lengths=lengths, ray_directions=directions, density_noise_std=noise_std, bg_color=bg_color,
+            rng_pass=pass_idx,
         )
         aux["weights"] = weights
         output = RendererOutput(features=features, depths=depths, alpha_masks=alpha_masks, aux=aux, prev_stage=prev_stage)
         if len(implicit_functions) > 1:
-            bundle: RayBundle = self._refiners[evaluation_mode](origins, directions, lengths, xys, weights)
+            bundle: RayBundle = self._refiners[evaluation_mode](origins, directions, lengths, xys, weights, rng_pass=pass_idx)
             output = self._run_raymarcher(*bundle, bg_color, implicit_functions[1:], output, evaluation_mode, **kwargs)
         return output

@@ -45,15 +45,18 @@ class RayPointRefiner(torch.nn.Module):
         self.random_sampling = random_sampling
         self.add_input_samples = add_input_samples
         self.last_flag: Optional[torch.Tensor] = None
+        self.device_rng = None  # ops.DeviceRng: uniforms drawn in the kernel instead of torch.rand
 
-    def forward(self, origins, directions, lengths, xys, ray_weights) -> RayBundle:
+    def forward(self, origins, directions, lengths, xys, ray_weights, rng_pass: int = 0) -> RayBundle:
         with torch.no_grad():
             lead, P = lengths.shape[:-1], lengths.shape[-1]
             z = lengths.reshape(-1, P)
             w = ray_weights.reshape(-1, P)
-            u = torch.rand(z.shape[0], self.n_pts_per_ray, device=z.device) if self.random_sampling else None
+            rng = self.device_rng if self.random_sampling else None
+            u = torch.rand(z.shape[0], self.n_pts_per_ray, device=z.device) if (self.random_sampling and rng is None) else None
             # the kernel takes the full weight row and uses weights[..., 1:-1] like the reference
-            z_new, _, flag = ops.sample_pdf_merge(z, w, self.n_pts_per_ray, u, self.add_input_samples)
+            z_new, _, flag = ops.sample_pdf_merge(z, w, self.n_pts_per_ray, u, self.add_input_samples, rng=rng,
+                                                  site=ops.DeviceRng.SITE_PDF + rng_pass)
             self.last_flag = flag
             if self.check_weights:
                 _raise_if_flagged(flag)

@@ -120,11 +120,30 @@ def eval_depth(pred, gt, crop: int = 0, mask=None, get_best_scale: bool = True, 
 class ViewMetrics(torch.nn.Module):
     """Per-image (shape `(B,)`) rgb mse / huber (+ optional depth abs error), keys prefixed."""
 
+    # ray counts per image up to this bound take the fused gather + loss kernel (one block per image: training batches);
+    # full-image evaluation grids use the torch ops
+    fused_max_rays: int = 65536
+
     def forward(self, image_sampling_grid, images=None, images_pred=None, depths=None, depths_pred=None,
                 loss_reweight_masks=None, keys_prefix: Optional[str] = "loss_", validate_grid: bool = True):
         pick = lambda t: None if t is None else sample_grid(t, image_sampling_grid, validate_grid)
-        images, depths, loss_reweight_masks = pick(images), pick(depths), pick(loss_reweight_masks)
         preds = {}
+        fused = (images is not None and images_pred is not None and loss_reweight_masks is None and images.is_cuda
+                 and images.ndim == 4 and images.shape[-1] == images_pred.shape[-1]
+                 and image_sampling_grid.numel() // (2 * images.shape[0]) <= self.fused_max_rays)
+        if fused:
+            # ground-truth gather + squared-error mean in one launch (and one for the backward): `yn_rgb_loss_fwd`
+            from yanerf import ops
+
+            if validate_grid:  # the reference's range assertions (two device->host syncs)
+                assert image_sampling_grid[..., 0].max() < images.shape[2], "Invalid ray_sampler.image_width"
+                assert image_sampling_grid[..., 1].max() < images.shape[1], "Invalid ray_sampler.image_height"
+            B = images.shape[0]
+            mse, hub = ops.rgb_loss(images_pred.reshape(B, -1, images_pred.shape[-1]), images,
+                                    image_sampling_grid.reshape(B, -1, 2))
+            preds.update({"rgb_huber": hub, "rgb_mse": mse})
+            images = None
+        images, depths, loss_reweight_masks = pick(images), pick(depths), pick(loss_reweight_masks)
         if images is not None and images_pred is not None:
             preds.update(_rgb_metrics(images, images_pred, loss_reweight_masks))
         if depths is not None and depths_pred is not None:

@@ -54,11 +54,15 @@ class FusedTrainer:
     """Owns flat parameter / gradient / Adam-moment buffers of a pipeline and performs one optimisation step."""
 
     def __init__(self, pipeline: torch.nn.Module, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group: Optional[Any] = None, use_cuda_graph: bool = False, graph_warmup_steps: int = 3) -> None:
+                 process_group: Optional[Any] = None, use_cuda_graph: bool = False, graph_warmup_steps: int = 3,
+                 device_rng: bool = True) -> None:
         """use_cuda_graph: after `graph_warmup_steps` eager steps the whole iteration (pixel pick, weight re-pack,
         forward, backward, Adam) is captured once and replayed; step counter, learning rate and the pixel seed live in
         device memory so every replay sees fresh values.  With several ranks the NCCL all-reduce and Adam follow the
-        replay as ordinary launches."""
+        replay as ordinary launches.
+        device_rng: the draws of the training forward (pixel pick, stratified jitter, density noise, inverse-CDF uniforms)
+        are generated inside the consuming kernels from one device-resident Philox state (`ops.DeviceRng`, seeded from
+        torch's CPU generator) instead of `torch.multinomial / rand / randn` tensors; False keeps torch's generators."""
         self.pipeline = pipeline
         self.use_cuda_graph = use_cuda_graph
         self._graph_warmup = graph_warmup_steps
@@ -100,6 +104,9 @@ class FusedTrainer:
         for m in pipeline.modules():  # O(n) graph-friendly pixel pick instead of torch.multinomial over H*W
             if hasattr(m, "fused_pixel_sampler"):
                 m.fused_pixel_sampler = True
+        self.rng = ops.DeviceRng(dev) if (device_rng and dev.type == "cuda" and hasattr(pipeline, "set_device_rng")) else None
+        if self.rng is not None:
+            pipeline.set_device_rng(self.rng)
         # no device->host sync inside the step: pixel-grid range checks move to the host (shapes) and the refiner's
         # "Negative weights provided." flag is ACCUMULATED on the device (flag |= this step's flags) and copied to pinned
         # memory after every step; the host looks at copies whose event has completed, so a flag raised by step k can
@@ -178,6 +185,8 @@ class FusedTrainer:
 
     def _eager_step(self, batch: Dict[str, Any], lr: Optional[float]) -> Dict[str, torch.Tensor]:
         self.zero_grad()
+        if self.rng is not None:
+            ops.step_begin(self.rng, None)
         preds = self._forward_backward(batch)
         self.optimizer_step(lr)
         return preds
@@ -268,16 +277,17 @@ class FusedTrainer:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph, stream=self._side_stream):
             self.flat_grad.zero_()
+            ops.step_begin(self.rng, self._state)  # snapshot of the draw step + Adam's device-side step counter
             preds = self._forward_backward(self._static_batch)
             if self.world == 1:
                 self._graph_optimizer()
             self._static_preds = {k: v.detach() if torch.is_tensor(v) else v for k, v in preds.items()}
 
     def _graph_optimizer(self) -> None:
-        """Adam with step count / learning rate read from device memory.  Single GPU: part of the captured graph.
+        """Adam with step count (bumped by `yn_step_begin` at the start of the captured step) / learning rate read from
+        device memory.  Single GPU: part of the captured graph.
         Multi-GPU: launched after the replay, behind the NCCL all-reduce (NCCL stays outside the capture: its
         watchdog and the capture do not mix reliably)."""
-        self._state[0:1] += 1.0
         ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._state, self.betas[0],
                           self.betas[1], self.eps, grad_scale=1.0 / self.world)
 
