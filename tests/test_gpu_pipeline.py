@@ -514,11 +514,15 @@ def test_ray_slab_sharded_render_equals_unsharded(monkeypatch):
         for rank in range(3):
             pipe.ray_shard = (rank, 3, None)
             out = pipe(**batch, evaluation_mode=EvaluationMode.EVALUATION)
-            for k in ("rendered_images", "rendered_depths", "rendered_alpha_masks"):
+            # without a process group the all-reduce is the identity: every emulated rank reports its slab's share
+            for k in ("rendered_images", "rendered_depths", "rendered_alpha_masks", "loss_rgb_mse", "loss_prev_stage_rgb_mse"):
                 acc[k] = out[k] if k not in acc else acc[k] + out[k]
         pipe.ray_shard = None
     for k, v in acc.items():
-        assert torch.equal(v, ref[k]), k
+        if k.startswith("rendered"):
+            assert torch.equal(v, ref[k]), k
+        else:  # slab sums of squared errors / n_rays add up to the full-image mean (fp32 summation order aside)
+            torch.testing.assert_close(v, ref[k], rtol=1e-5, atol=1e-8)
 
 
 def test_checkpoint_resume_continues_the_same_trajectory():

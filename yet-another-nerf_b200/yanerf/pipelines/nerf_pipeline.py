@@ -67,7 +67,8 @@ def slab_bounds(n_rays: int, world: int, rank: int, align: int = SLAB_ALIGN):
 
 
 def gather_slabs(local: torch.Tensor, n_rays: int, per: int, group=None) -> torch.Tensor:
-    """`[B, n_local, C]` (this rank's slab) -> `[B, n_rays, C]` on every rank."""
+    """`[B, n_local, C]` (this rank's slab) -> `[B, n_rays, C]` on every rank: ONE `all_gather_into_tensor` into a
+    preallocated `[world, B, per, C]` buffer."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -75,9 +76,18 @@ def gather_slabs(local: torch.Tensor, n_rays: int, per: int, group=None) -> torc
     world = dist.get_world_size(group)
     B, n_local, C = local.shape
     padded = local if n_local == per else torch.cat((local, local.new_zeros(B, per - n_local, C)), dim=1)
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded.contiguous(), group=group)
-    return torch.cat(parts, dim=1)[:, :n_rays]
+    out = local.new_empty(world, B, per, C)
+    dist.all_gather_into_tensor(out.view(-1), padded.contiguous().view(-1), group=group)
+    full = out.reshape(world * per, C)[None] if B == 1 else out.permute(1, 0, 2, 3).reshape(B, world * per, C)
+    return full[:, :n_rays]
+
+
+def reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 def _tensor_collator(batch, new_dims) -> torch.Tensor:
@@ -198,6 +208,9 @@ class NeRFPipeline(torch.nn.Module):
         training = evaluation_mode == EvaluationMode.TRAINING
         sampling_mode = RenderSamplingMode(self.sampling_mode_training if training else self.sampling_mode_evaluation)
         masked = sampling_mode == RenderSamplingMode.MASK_SAMPLE
+        if sampling_mode == RenderSamplingMode.FULL_GRID and self.ray_shard is not None and depth_map is None:
+            return self._forward_sharded(poses, focal_lengths, image_height, image_width, min_depth, max_depth,
+                                         bg_image_rgb, image_rgb, evaluation_mode, kwargs)
 
         ray_bundle: RayBundle = self.ray_sampler(
             poses, focal_lengths, evaluation_mode=evaluation_mode,
@@ -217,17 +230,7 @@ class NeRFPipeline(torch.nn.Module):
                     assert gh <= t.shape[-3], "Invalid ray_sampler.image_height"
         bg_color = sample_grid(bg_image_rgb, xys, validate) if bg_image_rgb is not None else None
 
-        extracted = collections.defaultdict(list)
-        for extractor in self.feature_extractors:
-            for k, v in extractor(**kwargs).items():
-                extracted[k].append(v)
-        for k, vs in extracted.items():
-            if isinstance(vs[0], torch.Tensor):
-                extracted[k] = torch.stack(vs, dim=1)
-            elif len(vs) != 1:
-                raise KeyError(f"{k} has multiple {type(vs[0])} values.")
-            else:
-                extracted[k] = vs[0]
+        extracted = self._extract_features(kwargs)
 
         for fn in self.implicit_functions:
             fn.bind_args(**extracted)
@@ -260,34 +263,84 @@ class NeRFPipeline(torch.nn.Module):
             preds["objective"] = objective
         return preds
 
+    def _extract_features(self, kwargs) -> Dict[str, Any]:
+        extracted = collections.defaultdict(list)
+        for extractor in self.feature_extractors:
+            for k, v in extractor(**kwargs).items():
+                extracted[k].append(v)
+        for k, vs in extracted.items():
+            if isinstance(vs[0], torch.Tensor):
+                extracted[k] = torch.stack(vs, dim=1)
+            elif len(vs) != 1:
+                raise KeyError(f"{k} has multiple {type(vs[0])} values.")
+            else:
+                extracted[k] = vs[0]
+        return extracted
+
     def _render(self, origins, directions, lengths, xys, *, bg_color, sampling_mode, **kwargs) -> RendererOutput:
-        if sampling_mode == RenderSamplingMode.FULL_GRID and self.ray_shard is not None:
-            return self._render_sharded(origins, directions, lengths, xys, bg_color=bg_color, sampling_mode=sampling_mode,
-                                        **kwargs)
         return self._render_local(origins, directions, lengths, xys, bg_color=bg_color, sampling_mode=sampling_mode,
                                   **kwargs)
 
-    def _render_sharded(self, origins, directions, lengths, xys, *, bg_color, **kwargs) -> RendererOutput:
+    def _forward_sharded(self, poses, focal_lengths, image_height, image_width, min_depth, max_depth, bg_image_rgb,
+                         image_rgb, evaluation_mode, kwargs) -> Dict[str, Any]:
+        """Full-grid forward with the H*W ray list cut into one contiguous slab per rank: this rank
+        generates, renders and scores ONLY its slab; then one all-gather of `[slab, 2 x (C + 2)]` (both stages' rgb, depth,
+        alpha) rebuilds the images on every rank and one all-reduce of the per-image squared-error sums gives the losses.
+        The images are bit-identical to the unsharded render (rays are independent, slabs are whole MLP tiles); the losses
+        agree up to the fp32 summation order."""
+        from .utils import huber
+
         rank, world, group = self.ray_shard
-        B, *spatial, P = lengths.shape
-        n_rays = math.prod(spatial)
+        custom = image_height is not None and image_width is not None
+        Hh, Ww = (image_height, image_width) if custom else (self.render_image_height, self.render_image_width)
+        n_rays = Hh * Ww
         start, end, per = slab_bounds(n_rays, world, rank)
-        flat = lambda t: None if t is None else t.reshape(B, n_rays, 1, t.shape[-1])[:, start:end]
-        stages = []
-        if end > start:
-            out = self._render_local(flat(origins), flat(directions), flat(lengths), flat(xys), bg_color=flat(bg_color),
-                                     **kwargs)
+        B = poses.shape[0]
+        validate = self.validate_pixel_grid
+        n_local = end - start
+        stages: List[torch.Tensor] = []
+        sums: Dict[str, torch.Tensor] = {}
+        channels = None
+        if n_local > 0:
+            bundle: RayBundle = self.ray_sampler(
+                poses, focal_lengths, evaluation_mode=evaluation_mode, image_height=image_height, image_width=image_width,
+                min_depth=min_depth, max_depth=max_depth, ray_range=(start, end))
+            xys = bundle.xys
+            bg_color = sample_grid(bg_image_rgb, xys, validate) if bg_image_rgb is not None else None
+            extracted = self._extract_features(kwargs)
+            for fn in self.implicit_functions:
+                fn.bind_args(**extracted)
+            try:
+                out = self._render_local(*bundle, bg_color=bg_color, sampling_mode=RenderSamplingMode.FULL_GRID,
+                                         implicit_functions=self.implicit_functions, evaluation_mode=evaluation_mode)
+            finally:
+                for fn in self.implicit_functions:
+                    fn.unbind_args()
+            local = self._get_view_metrics(raymarched=out, xys=xys, image_rgb=image_rgb, depth_map=None, validate_grid=validate)
+            sums = {k: v * float(n_local) for k, v in local.items() if k.endswith("rgb_mse")}  # per-slab mean -> sum
             while out is not None:
-                stages.append(torch.cat((out.features, out.depths, out.alpha_masks), dim=-1).reshape(B, end - start, -1))
+                stages.append(torch.cat((out.features, out.depths, out.alpha_masks), dim=-1).reshape(B, n_local, -1))
                 out = out.prev_stage
-        else:  # more ranks than slabs: contribute an empty slab per stage
-            stages = [lengths.new_zeros(B, 0, 5) for _ in range(self.num_passes)]
-        result = None
-        for packed in reversed(stages):  # coarsest stage first, so that prev_stage chains like the renderer's output
-            full = gather_slabs(packed, n_rays, per, group).reshape(B, *spatial, packed.shape[-1])
-            result = RendererOutput(features=full[..., :-2], depths=full[..., -2:-1], alpha_masks=full[..., -1:],
-                                    prev_stage=result)
-        return result
+            channels = stages[0].shape[-1]
+        if channels is None:  # more ranks than slabs: an empty contribution of the right width
+            channels = int(self.bg_color.numel() if self.bg_color.numel() > 1 else 3) + 2
+            stages = [poses.new_zeros(B, 0, channels) for _ in range(self.num_passes)]
+        packed = torch.cat(stages, dim=-1)  # finest stage first
+        full = gather_slabs(packed, n_rays, per, group).reshape(B, Hh, Ww, packed.shape[-1])
+        preds: Dict[str, Any] = {}
+        if image_rgb is not None:
+            keys = ["loss_" + "prev_stage_" * k + "rgb_mse" for k in range(len(stages))]
+            acc = torch.stack([sums.get(k, poses.new_zeros(B)) for k in keys])
+            acc = reduce_sum(acc.contiguous(), group) / float(n_rays)
+            for k, v in zip(keys, acc):
+                preds[k] = v
+                preds[k.replace("rgb_mse", "rgb_huber")] = huber(v, scaling=0.03)
+        fine = full[..., :channels]
+        preds.update(rendered_images=fine[..., :-2], rendered_depths=fine[..., -2:-1], rendered_alpha_masks=fine[..., -1:])
+        objective = self._get_objective(preds)
+        if objective is not None:
+            preds["objective"] = objective
+        return preds
 
     def _render_local(self, origins, directions, lengths, xys, *, bg_color, sampling_mode, **kwargs) -> RendererOutput:
         if sampling_mode == RenderSamplingMode.FULL_GRID and self.chunk_size_grid > 0:

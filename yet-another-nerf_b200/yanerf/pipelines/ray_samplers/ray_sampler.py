@@ -52,6 +52,20 @@ def _depth_row(min_depth: float, max_depth: float, n: int, device) -> torch.Tens
     return _DEPTH_ROWS[key]
 
 
+_PIXEL_GRIDS = {}
+
+
+def _pixel_grid(H: int, W: int, device) -> torch.Tensor:
+    """Float pixel coordinates (x, y) of the flattened H x W grid, [H*W, 2], cached per device."""
+    key = (H, W, str(device))
+    if key not in _PIXEL_GRIDS:
+        if len(_PIXEL_GRIDS) > 16:
+            _PIXEL_GRIDS.clear()
+        idx = torch.arange(H * W, device=device)
+        _PIXEL_GRIDS[key] = torch.stack((idx % W, idx // W), dim=-1).float()
+    return _PIXEL_GRIDS[key]
+
+
 class _RaySampler(torch.nn.Module):
     def __init__(self, *, image_width: int, image_height: int, n_pts_per_ray: int, min_depth: float,
                  max_depth: float, n_rays_per_image: Optional[int] = None, unit_directions: bool = False,
@@ -77,7 +91,9 @@ class _RaySampler(torch.nn.Module):
     def forward(self, poses, focal_lengths, *, image_height=None, image_width=None, mask=None,
                 sampling_prob_mask=None, min_depth=None, max_depth=None,
                 n_rays_per_image: Union[None, int, List[int]] = None, n_pts_per_ray=None,
-                stratified_sampling=None) -> RayBundle:
+                stratified_sampling=None, ray_range: Optional[Tuple[int, int]] = None) -> RayBundle:
+        """ray_range=(start, end): full-grid mode only: the rays of flat pixels [start, end) instead of the whole H x W
+        grid, spatial shape (end - start, 1) (one rank's slab of a ray-sharded render)."""
         B = poses.shape[0]
         device = poses.device
         poses = poses[:, :3, :4]
@@ -158,6 +174,10 @@ class _RaySampler(torch.nn.Module):
         n_pts = self._n_pts_per_ray if n_pts_per_ray is None else n_pts_per_ray
         stratified = self._stratified_sampling if stratified_sampling is None else stratified_sampling
 
+        if ray_range is not None and xy is None:
+            start, end = ray_range
+            xy = _pixel_grid(H, W, device)[start:end][None].expand(B, -1, -1).contiguous()
+            spatial = (end - start, 1)
         n = spatial[0] * spatial[1]
         depths = _depth_row(min_depth, max_depth, n_pts, device)
         u = torch.rand(B, n, n_pts, device=device) if (stratified and n_pts > 0) else None
@@ -230,7 +250,7 @@ class RaySampler(torch.nn.Module):
 
     def forward(self, poses, focal_lengths, evaluation_mode: EvaluationMode, *, mask=None, sampling_prob_mask=None,
                 image_height=None, image_width=None, min_depth=None, max_depth=None,
-                n_rays_per_image: Union[None, int, List[int]] = None) -> RayBundle:
+                n_rays_per_image: Union[None, int, List[int]] = None, ray_range: Optional[Tuple[int, int]] = None) -> RayBundle:
         sample_mask = None
         if self._sampling_mode[evaluation_mode] == RenderSamplingMode.MASK_SAMPLE and mask is not None:
             h = self.image_height if image_height is None or image_width is None else image_height
@@ -241,4 +261,5 @@ class RaySampler(torch.nn.Module):
         return self._raysamplers[evaluation_mode](
             poses, focal_lengths, mask=sample_mask, sampling_prob_mask=sampling_prob_mask, min_depth=min_depth,
             max_depth=max_depth, n_rays_per_image=n_rays_per_image, image_height=image_height, image_width=image_width,
+            ray_range=ray_range,
         )
