@@ -606,6 +606,8 @@ def _main():
     ap.add_argument("--only", default="", help="comma list of sub-records to run besides the headline: "
                                                "train,strong,fern,micro,eager,cpu (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", default="", choices=["", "train", "render", "micro"],
+                    help="profiling aid (ncu launch lists / --set full): run ONLY this workload, eagerly, for --steps steps")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -626,6 +628,17 @@ def _main():
     want = set(filter(None, args.only.split(","))) or {"train", "strong", "fern", "micro", "eager", "cpu"}
     if args.no_cpu_baseline:
         want.discard("cpu")
+    if args.profile:
+        if args.profile == "train":
+            os.environ["YANERF_TRAIN_GRAPH"] = "0"  # eager launches: every kernel is visible to the profiler
+            rec = bench_train(ctx, LEGO, max(1, args.steps))
+        elif args.profile == "render":
+            rec, _ = bench_render(ctx, LEGO, max(1, args.steps), args.warmup, want_roofline=False)
+        else:
+            rec = bench_microbench(dev)
+        if rank == 0:
+            emit({"profile": args.profile, **rec})
+        return
 
     head, pipe = bench_render(ctx, LEGO, args.steps, args.warmup, want_roofline=True)
     line = dict(

@@ -1,3 +1,3 @@
-from yanerf.utils.registry import Registry
+from ..utils.registry import Registry
 
 PIPELINES = Registry("pipelines")

@@ -1,3 +1,3 @@
-from yanerf.utils.registry import Registry
+from ...utils.registry import Registry
 
 FEATURE_EXTRACTORS = Registry("feature_extractors")

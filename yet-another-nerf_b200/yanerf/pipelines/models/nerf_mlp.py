@@ -14,9 +14,9 @@ from typing import List, Optional
 
 import torch
 
-from yanerf import _native as N
-from yanerf import ops
-from yanerf.utils.logging import get_logger
+from ... import _native as N
+from ... import ops
+from ...utils.logging import get_logger
 
 from .builder import MODELS
 

@@ -18,14 +18,14 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Union
 
 import torch
 
-from yanerf.pipelines.feature_extractors import FEATURE_EXTRACTORS
-from yanerf.pipelines.models import MODELS
-from yanerf.pipelines.ray_samplers import RAY_SAMPLERS
-from yanerf.pipelines.ray_samplers.utils import RayBundle, RenderSamplingMode
-from yanerf.pipelines.renderers import RENDERERS
-from yanerf.pipelines.renderers.utils import RendererOutput
-from yanerf.pipelines.utils import EvaluationMode
-from yanerf.utils.logging import get_logger
+from ..pipelines.feature_extractors import FEATURE_EXTRACTORS
+from ..pipelines.models import MODELS
+from ..pipelines.ray_samplers import RAY_SAMPLERS
+from ..pipelines.ray_samplers.utils import RayBundle, RenderSamplingMode
+from ..pipelines.renderers import RENDERERS
+from ..pipelines.renderers.utils import RendererOutput
+from ..pipelines.utils import EvaluationMode, as_mode
+from ..utils.logging import get_logger
 
 from .builder import PIPELINES
 from .utils import PartialFunctionWrapper, ViewMetrics, sample_grid, scatter_rays_to_image
@@ -205,6 +205,7 @@ class NeRFPipeline(torch.nn.Module):
         evaluation_mode: EvaluationMode = EvaluationMode.EVALUATION,
         **kwargs,
     ) -> Dict[str, Any]:
+        evaluation_mode = as_mode(evaluation_mode)
         training = evaluation_mode == EvaluationMode.TRAINING
         sampling_mode = RenderSamplingMode(self.sampling_mode_training if training else self.sampling_mode_evaluation)
         masked = sampling_mode == RenderSamplingMode.MASK_SAMPLE
@@ -385,7 +386,7 @@ class NeRFPipeline(torch.nn.Module):
         vals = list(rendered_dict.values())
         if bg_color is None and xys.is_cuda and 1 <= len(vals) <= 3:
             # one zero fill + one launch for rgb / depth / alpha together (`yn_scatter_rays`)
-            from yanerf import ops
+            from .. import ops
 
             with torch.no_grad():
                 B = xys.shape[0]

@@ -11,9 +11,10 @@ from typing import List, Optional, Tuple, Union
 
 import torch
 
-from yanerf import ops
+from ... import ops
 
 from .builder import RAY_SAMPLERS
+from ...pipelines.utils import as_mode
 from .utils import EvaluationMode, RayBundle, RenderSamplingMode
 
 
@@ -251,6 +252,7 @@ class RaySampler(torch.nn.Module):
     def forward(self, poses, focal_lengths, evaluation_mode: EvaluationMode, *, mask=None, sampling_prob_mask=None,
                 image_height=None, image_width=None, min_depth=None, max_depth=None,
                 n_rays_per_image: Union[None, int, List[int]] = None, ray_range: Optional[Tuple[int, int]] = None) -> RayBundle:
+        evaluation_mode = as_mode(evaluation_mode)
         sample_mask = None
         if self._sampling_mode[evaluation_mode] == RenderSamplingMode.MASK_SAMPLE and mask is not None:
             h = self.image_height if image_height is None or image_width is None else image_height

@@ -3,7 +3,7 @@ from enum import Enum
 
 import torch
 
-from yanerf.pipelines.utils import EvaluationMode, RayBundle  # noqa: F401  (re-exported like the reference)
+from ...pipelines.utils import EvaluationMode, RayBundle  # noqa: F401  (re-exported like the reference)
 
 
 class RenderSamplingMode(Enum):

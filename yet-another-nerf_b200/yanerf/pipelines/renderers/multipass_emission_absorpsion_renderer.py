@@ -10,8 +10,8 @@ from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
 import torch
 
-from yanerf import ops
-from yanerf.pipelines.utils import EvaluationMode, RayBundle
+from ... import ops
+from ...pipelines.utils import EvaluationMode, RayBundle, as_mode
 
 from .builder import RENDERERS
 from .utils import RayPointRefiner, RendererOutput
@@ -122,7 +122,7 @@ class MultipassEmissionAbsorpsionRenderer(torch.nn.Module):
         if not implicit_functions:
             raise ValueError("EA renderer expects implicit functions")
         return self._run_raymarcher(origins, directions, lengths, xys, bg_color, implicit_functions, None,
-                                    evaluation_mode, **kwargs)
+                                    as_mode(evaluation_mode), **kwargs)
 
     def set_device_rng(self, rng) -> None:
         """In-kernel draws (ops.DeviceRng) for the density noise and the refiners' inverse-CDF uniforms; None switches

@@ -10,8 +10,8 @@ from typing import Any, Dict, Optional
 
 import torch
 
-from yanerf import ops
-from yanerf.pipelines.utils import RayBundle
+from ... import ops
+from ...pipelines.utils import RayBundle
 
 
 @dataclass

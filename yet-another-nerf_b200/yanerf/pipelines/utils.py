@@ -18,6 +18,12 @@ class EvaluationMode(Enum):
     EVALUATION = "evaluation"
 
 
+def as_mode(mode) -> "EvaluationMode":
+    """Accepts this package's enum, its value string, or the enum of ANOTHER copy of the package (the
+    reference's `yanerf.pipelines.utils.EvaluationMode` when our classes are registered into the reference's registries)."""
+    return mode if isinstance(mode, EvaluationMode) else EvaluationMode(getattr(mode, "value", mode))
+
+
 class RayBundle(NamedTuple):
     origins: torch.Tensor
     directions: torch.Tensor
@@ -133,7 +139,7 @@ class ViewMetrics(torch.nn.Module):
                  and image_sampling_grid.numel() // (2 * images.shape[0]) <= self.fused_max_rays)
         if fused:
             # ground-truth gather + squared-error mean in one launch (and one for the backward): `yn_rgb_loss_fwd`
-            from yanerf import ops
+            from .. import ops
 
             if validate_grid:  # the reference's range assertions (two device->host syncs)
                 assert image_sampling_grid[..., 0].max() < images.shape[2], "Invalid ray_sampler.image_width"

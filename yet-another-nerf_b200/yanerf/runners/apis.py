@@ -11,7 +11,7 @@ from typing import Any, Dict, Iterable, Optional
 import torch
 import torch.distributed as dist
 
-from yanerf.pipelines.utils import EvaluationMode
+from ..pipelines.utils import EvaluationMode
 
 from .engine import FusedTrainer, reference_lr, scaled_runner_config
 

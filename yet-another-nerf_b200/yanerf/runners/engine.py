@@ -15,8 +15,8 @@ from typing import Any, Callable, Dict, List, Optional
 import torch
 import torch.distributed as dist
 
-from yanerf import ops
-from yanerf.pipelines.utils import EvaluationMode
+from .. import ops
+from ..pipelines.utils import EvaluationMode
 
 
 def reference_lr(it: int, *, init_lr: float, min_lr: float, lr_decay_type: str = "exponential", lr_decay_rate: float = 0.1,
