@@ -44,7 +44,9 @@ struct BwdParams {
   int64_t n_points;
   int64_t R;
   int P;
-  int debug;  // YN_BWD_DEBUG bits >= 16 (timing experiments)
+  int debug;  // YN_BWD_DEBUG (timing experiments, tools/bwd_split*.sh): 1/2/4/8 skip dgrad / wgrad / heads / direction; 16 heads without
+              // prefetch; 32 / 64 gradient-stash writes / wgrad reads in an L2-resident window; 128 no masks; 256 no gradient-stash
+              // stores; 512 wgrad without operand copies; 1024 wgrad without the small (embedding / ones) MMAs
 };
 
 __device__ __forceinline__ void bwd_named_bar_sync(int id, int nthreads) {
@@ -224,11 +226,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
-      const bool tile_live = tile < n_tiles;
+      const bool tile_real = tile < n_tiles;
+      const bool tile_live = tile_real && !(p.debug & 256);  // (bit 256, timing experiment: no gradient-stash stores)
       const int64_t gidx = tile * kTileM + row;
       const bool valid = gidx < p.n_points;
       // rows of partner tiles beyond the end alias tile 0 of the stash for reads; their gradients are zero
-      const int64_t rtile = tile_live ? tile : 0;
+      const int64_t rtile = tile_real ? tile : 0;
       // this row's ReLU sign masks (32 B per layer): mask m at A.mask_offset(m)
       const uint8_t* mask_rows = p.stash + (size_t)rtile * blocks_per_tile * kBlkBytes + (size_t)row * 32;
       // (YN_BWD_DEBUG bit 32, timing experiment: every gradient-stash store lands in a 64-tile window that stays in L2)
@@ -308,7 +311,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         }
         bwd_named_bar_sync(1 + g, 128);
         // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
-        if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
+        if (p.debug & 128) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mk0, swz, dd, wd, g_row);  // (timing experiment: no masks)
+        else if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mk0, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
@@ -330,7 +334,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         if (leader) bulk_wait_read<1>();  // the previous step's blocks-2,3 store (most recent group: this step's blocks 0,1)
         bwd_named_bar_sync(1 + g, 128);
         // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
-        if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
+        if (p.debug & 128) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mk1, swz, dd, wd, g_row);
+        else if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mk1, swz, dd, wd, g_row);
         tc_fence_before();
         fence_proxy_async_smem();
@@ -429,6 +434,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
         const uint32_t dst = smem_base + slot * kWgStageBytes;
         const uint32_t bar = bar_full + 8 * slot;
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        if (p.debug & 512) {  // (timing experiment: no operand copies, the MMA pipeline alone)
+          mbar_arrive(bar);
+          if (++slot == kWgStages) { slot = 0; phase ^= 1; }
+          continue;
+        }
         mbar_arrive_expect_tx(bar, stage_bytes);
         bulk_g2s(dst, gs + (size_t)(A.stash_block_of_layer(l) + 2 * mh) * kBlkBytes, 2 * kBlkBytes, bar);
         if (has_hidden) bulk_g2s(dst + 2 * kBlkBytes, st + (size_t)A.stash_block_of_layer(xprev) * kBlkBytes, 4 * kBlkBytes, bar);
@@ -454,8 +464,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
           const uint64_t a_desc = umma_desc_mnmajor(base + k * 2048);
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
           if (has_hidden) umma_f16(tmem_base, a_desc, umma_desc_mnmajor(base + 2 * kBlkBytes + k * 2048), idesc256, acc);
-          if (has_emb) umma_f16(tmem_base + 256, a_desc, umma_desc_mnmajor(base + 6 * kBlkBytes + k * 2048), idesc64, acc);
-          if (use_ones) umma_f16(tmem_base + 320, a_desc, ones_desc, idesc16, acc);
+          if (has_emb && !(p.debug & 1024)) umma_f16(tmem_base + 256, a_desc, umma_desc_mnmajor(base + 6 * kBlkBytes + k * 2048), idesc64, acc);
+          if (use_ones && !(p.debug & 1024)) umma_f16(tmem_base + 320, a_desc, ones_desc, idesc16, acc);  // (1024: timing experiment)
         }
         first = 0;
         umma_commit(bar_empty + 8 * slot);

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       const int64_t ray = valid ? gidx / p.P : 0;
       // (YN_FWD_DEBUG bit 4, timing experiment: every stash store lands in a 64-tile window that stays in L2)
       uint8_t* stash_tile = kStash ? p.stash + (size_t)((p.debug & 4) ? tile % 64 : tile) * blocks_per_tile * kBlkBytes : nullptr;
-      const bool tile_live = tile < n_tiles;
+      const bool tile_live = tile < n_tiles && !(kStash && (p.debug & 16));  // (bit 16, timing experiment: no stash stores)
 
       if (kStash) {
         if (stash_leader) bulk_wait_read<0>();
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         const bool plain = !is_color;
         // ReLU sign mask of this layer and row (training only): trunk layer l -> mask l, colour hidden -> mask n_layers
         uint8_t* mask_row = nullptr;
-        if (kStash && tile_live)
+        if (kStash && tile_live && !(p.debug & 8))  // (bit 8, timing experiment: no sign masks)
           mask_row = stash_tile + A.mask_offset(is_color ? A.n_layers : l) + (size_t)row * 32;
         if (p.debug & 1) {
           before_store0();
