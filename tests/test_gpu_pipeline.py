@@ -218,22 +218,23 @@ def test_train_forward_backward_vs_reference_golden(golden, tag, n_fine, std, ga
         assert float((got - ref).abs().max()) <= tol, (k, got, ref)
     if gain == 1.0:
         err = float((preds["rendered_images"].cpu() - T(g[f"{tag}_train_rendered_images"])).abs().max())
-        assert err <= 4e-3, err  # bf16 operands in training
+        print(tag, "training forward (replayed draws): rendered rgb max abs err", err)
+        assert err <= (2e-3 if n_fine == 64 else 3e-3), err  # same bound as the evaluation render: fp16 operands in both
     preds["objective"].mean().backward()
     # Every one of the 2 x 24 parameter tensors against the reference's autograd (golden summaries: sum, sum|.|, L2 norm;
-    # three tensors in full).  The kernels run the layers with bf16 operands (8-bit mantissa) where the reference runs
-    # fp32, so a fraction of the ReLU units has the opposite sign (test_mlp_backward_vs_oracle_autograd quantifies it per
-    # layer).  Bounds at xavier scale ("fern", "lego1"): per-tensor L2 norm and sum|.| within 3 %, the signed sum within
-    # 3 % of sum|.| (measured worst: 2.9 % on the first layer's bias, the far end of the backward chain; <= 1.4 % on every
-    # weight matrix); the density head (a strongly cancelling sum of d(loss)/d(sigma) over all points of all rays) within
-    # 6 % (measured 4.6 %); full tensors cos >= 0.985 (measured >= 0.9879).  The x3 stress weights ("lego") are chaotic (see the eval test): gradients there
-    # are only required to be finite.
+    # three tensors in full).  The kernels run the layers with fp16 operands (11-bit significand) where the reference runs
+    # fp32, so a small fraction of the ReLU units has the opposite sign (test_mlp_backward_vs_oracle_autograd quantifies it
+    # per layer).  Bounds at xavier scale ("fern", "lego1"): per-tensor L2 norm and sum|.| within 2 %, the signed sum within
+    # 2 % of sum|.| (measured worst: 0.96 %); the density head within 6 % (measured 4.3 % in the noise configuration: its
+    # gradient sums d(loss)/d(sigma) over the samples whose noisy density is positive, and relu(sigma + noise) flips with the
+    # 3e-4 error of sigma); full tensors cos >= 0.995 (measured >= 0.9971).  The x3 stress weights ("lego") are chaotic (see
+    # the eval test): gradients there are only required to be finite.
     if gain != 1.0:
         for fn in pipe.implicit_functions:
             for name, p in fn._fn.named_parameters():
                 assert p.grad is not None and torch.isfinite(p.grad).all(), name
         return
-    k_norm, k_cos = 0.03, 0.985
+    k_norm, k_cos = 0.02, 0.995
     worst = dict(norm=0.0, l1=0.0, sum=0.0)
     failures = []
     for k, fn in enumerate(pipe.implicit_functions):
@@ -250,7 +251,7 @@ def test_train_forward_backward_vs_reference_golden(golden, tag, n_fine, std, ga
             e_sum = abs(float(gk.sum()) - rsum) / rl1
             print(f"  {tag} net{k} {name:36s} norm {rnorm:9.3e} dev {e_norm:7.4f}  sum|.| dev {e_l1:7.4f}  sum dev/sum|.| {e_sum:7.4f}")
             worst = dict(norm=max(worst["norm"], e_norm), l1=max(worst["l1"], e_l1), sum=max(worst["sum"], e_sum))
-            tol = 2 * k_norm if name.startswith("density_layer") else k_norm
+            tol = 3 * k_norm if name.startswith("density_layer") else k_norm
             if not (e_norm <= tol and e_l1 <= tol and e_sum <= tol):
                 failures.append((tag, k, name, round(e_norm, 4), round(e_l1, 4), round(e_sum, 4)))
         m = fn._fn

@@ -46,7 +46,7 @@ def test_size_queries_and_validation_without_gpu():
     assert lib.yn_mlp_aux_floats(ctypes.byref(lego)) == 9 * 256 + 256 + 4 + 512 + 4 + 128 * 256 + 128
     # per 128-point tile: embedding block, 9 x 4 + 2 activation blocks, 3 blocks holding the nine 4 KB ReLU sign masks
     assert lib.yn_mlp_stash_bytes(ctypes.byref(lego), 1000) == 8 * (1 + 36 + 2 + 3) * 16384
-    assert lib.yn_mlp_bwd_workspace_bytes(ctypes.byref(lego), 1000) == 8 * 42 * 16384 + (128 * 256 + 128) * 4
+    assert lib.yn_mlp_bwd_workspace_bytes(ctypes.byref(lego), 1000) == 8 * 42 * 16384 + (128 * 256 + 128 + 4) * 4
     bad = N.MlpArch(8, 1 << 5, 12, 4, 256, 128, 3, N.FMT_FP16)  # 75-channel embedding
     assert lib.yn_mlp_param_count(ctypes.byref(bad)) == -1
     assert b"embedding" in lib.yn_last_error_string()

@@ -41,6 +41,7 @@ struct BwdParams {
   uint8_t* gstash;
   float* grads;
   float* tbuf;  // [128][256] fp32: T = dY_colour^T relu(h_last) (see mlp_bwd_inter_kernel); then [128] column sums of dY_colour
+  const float* amax;  // max |d_density|, |d_rgb| of this call (grad_amax_kernel); the fp16 gradient scale derives from it
   int64_t n_points;
   int64_t R;
   int P;
@@ -71,6 +72,34 @@ __device__ __forceinline__ void mask_quad(uint32_t w, int j, uint32_t& p0, uint3
   const uint32_t s = t * 0x10204080u;               // byte 3 msb = column j, byte 2 = j + 1, byte 1 = j + 2, byte 0 = j + 3
   p0 &= ~prmt(s, 0u, 0xAABBu);                      // low half <- sign(byte 3), high half <- sign(byte 2)
   p1 &= ~prmt(s, 0u, 0x8899u);                      // low half <- sign(byte 1), high half <- sign(byte 0)
+}
+
+// fp16 operands (kFmt 0) have 5 exponent bits: gradients d(loss)/d(activation) of a mean-reduced loss over thousands of rays
+// (1e-6 .. 1e-9) would sit in or below the subnormal range.  Every 16-bit gradient of one backward call is therefore carried
+// multiplied by ONE power of two S, chosen from the largest incoming gradient so that it lands at 2^-4 .. 2^-5 (20 binades
+// of headroom for growth through the layers, 20 below before precision is lost), and every fp32 flush multiplies by 1/S:
+// exact, since S is a power of two and all accumulation is fp32.  bf16 (kFmt 1) has fp32's exponent range: S = 1.
+template <int kFmt>
+__device__ __forceinline__ float grad_scale(const BwdParams& p) {
+  if (kFmt == 1) return 1.f;
+  const float a = *p.amax;
+  if (!(a > 0.f) || !(a < 3.0e38f)) return 1.f;
+  float e = -ceilf(log2f(a)) - 4.f;
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
+
+__global__ void __launch_bounds__(256) grad_amax_kernel(const float* __restrict__ d_density, const float* __restrict__ d_rgb,
+                                                        int64_t n_points, int C, float* amax) {
+  float m = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += stride) {
+    m = fmaxf(m, fabsf(__ldg(d_density + i)));
+    for (int c = 0; c < C; ++c) m = fmaxf(m, fabsf(__ldg(d_rgb + i * C + c)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));  // non-negative floats order like uints
 }
 
 // epilogue of one 128-column half of a data-gradient step.
@@ -222,6 +251,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
     const float* wd = p.aux + A.aux_wd();
     const float* w2 = p.aux + A.aux_w2();
     const int C = A.color_dim;
+    const float gscale = grad_scale<kFmt>(p);  // every 16-bit gradient of this call is carried times this power of two
     uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -243,10 +273,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       float ds[4] = {0.f, 0.f, 0.f, 0.f};
       float dd = 0.f;
       if (valid) {
-        dd = __ldg(p.d_density + gidx);
+        dd = __ldg(p.d_density + gidx) * gscale;
         for (int c = 0; c < C; ++c) {
           const float y = __ldg(p.rgb + gidx * C + c);
-          ds[c] = __ldg(p.d_rgb + gidx * C + c) * y * (1.f - y);
+          ds[c] = __ldg(p.d_rgb + gidx * C + c) * y * (1.f - y) * gscale;
         }
       }
       {
@@ -481,6 +511,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     mbar_wait(bar_done, 0);
     tc_fence_after();
+    const float inv = 1.f / grad_scale<kFmt>(p);  // the accumulators hold S * gradient (exact un-scaling: S is a power of two)
     const int dout = A.dout(l), din = A.din(l), hin = A.hidden_in(l), exyz = A.embed_xyz();
     float* W = color_job ? p.tbuf + (int64_t)out * kInner : p.grads + A.w_offset(l) + (int64_t)out * din;
     float* bgrad = p.grads + A.b_offset(l) + out;
@@ -493,7 +524,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
         if (row_ok)
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (cb * 32 + j < hin) atomicAdd(W + cb * 32 + j, __uint_as_float(v[j]));
+            if (cb * 32 + j < hin) atomicAdd(W + cb * 32 + j, __uint_as_float(v[j]) * inv);
       }
     }
     if (has_emb) {
@@ -505,8 +536,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int e = cb * 32 + j;
-            if (e < exyz) atomicAdd(W + hin + e, __uint_as_float(v[j]));
-            else if (e == 63) atomicAdd(bgrad, __uint_as_float(v[j]));  // constant-1 channel -> bias
+            if (e < exyz) atomicAdd(W + hin + e, __uint_as_float(v[j]) * inv);
+            else if (e == 63) atomicAdd(bgrad, __uint_as_float(v[j]) * inv);  // constant-1 channel -> bias
           }
       }
     }
@@ -515,8 +546,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
       tmem_ld32(t_row + 320, v);  // columns 320..335 hold 16 identical sums (the rest is unused)
       tmem_ld_wait();
       if (row_ok) {
-        atomicAdd(bgrad, __uint_as_float(v[0]));
-        if (color_job) atomicAdd(p.tbuf + kDirPad * kInner + out, __uint_as_float(v[0]));
+        atomicAdd(bgrad, __uint_as_float(v[0]) * inv);
+        if (color_job) atomicAdd(p.tbuf + kDirPad * kInner + out, __uint_as_float(v[0]) * inv);
       }
     }
   }
@@ -719,10 +750,11 @@ __global__ void __launch_bounds__(256) mlp_bwd_dir_kernel(const BwdParams p) {
       for (int i = 0; i < 4; ++i) acc[i][k] = fmaf(gsum[i], e, acc[i][k]);
     }
   }
+  const float inv = 1.f / grad_scale<kFmt>(p);  // the gradient stash holds S * dY
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k < kE; ++k) atomicAdd(&s_acc[(c0 + i) * kE + k], acc[i][k]);
+    for (int k = 0; k < kE; ++k) atomicAdd(&s_acc[(c0 + i) * kE + k], acc[i][k] * inv);
   __syncthreads();
   const int din = A.din(n + 1);
   float* W = p.grads + A.w_offset(n + 1);
@@ -791,7 +823,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_inter_kernel(const BwdParams p) {
   }
 }
 
-constexpr size_t kTbufBytes = (size_t)(kDirPad * kInner + kDirPad) * sizeof(float);
+constexpr size_t kTbufBytes = (size_t)(kDirPad * kInner + kDirPad + 4) * sizeof(float);  // T, column sums, then the gradient amax word
 
 static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
   const Arch& A = p.arch;
@@ -813,6 +845,8 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
     // YN_BWD_DEBUG (timing experiments only, wrong gradients; tools/bwd_split.sh): bit mask of kernels to skip
     const int skip = p.debug;
     cudaMemsetAsync(p.tbuf, 0, kTbufBytes, stream);
+    if (A.fmt == 0)  // fp16 operands: find the scale of this call's 16-bit gradients (see grad_scale)
+      grad_amax_kernel<<<2 * sms, 256, 0, stream>>>(p.d_density, p.d_rgb, p.n_points, A.color_dim, const_cast<float*>(p.amax));
     if (!(skip & 1)) dgrad<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(p);
     if (!(skip & 2)) {
       wgrad<<<n_jobs * n_splits, kWgThreads, kWgSmemBytes, stream>>>(p, n_jobs, n_splits);
@@ -865,6 +899,7 @@ extern "C" int yn_mlp_bwd(const yn_mlp_arch* arch, const float* directions, cons
   p.stash = static_cast<const uint8_t*>(stash);
   p.gstash = static_cast<uint8_t*>(workspace);
   p.tbuf = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + yn_mlp_stash_bytes(arch, R * P));
+  p.amax = p.tbuf + ynb::kDirPad * ynb::kInner + ynb::kDirPad;
   p.grads = grads;
   p.n_points = R * P;
   p.R = R;

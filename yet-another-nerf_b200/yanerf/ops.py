@@ -23,7 +23,7 @@ class Profiler:
     enabled = False
     records: list = []
     launches = 0
-    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 3, "yn_mlp_bwd": 5}  # bwd: dgrad, wgrad, inter, heads, direction
+    KERNELS_PER_CALL = {"yn_mlp_pack_weights": 3, "yn_mlp_bwd": 6}  # bwd: gradient amax, dgrad, wgrad, inter, heads, direction
 
     @classmethod
     def reset(cls):

@@ -55,10 +55,13 @@ _FMT = {"fp16": N.FMT_FP16, "bf16": N.FMT_BF16}
 
 
 def _default_fmt(training: bool) -> int:
-    """Tensor-core operand type.  Inference: fp16 (10-bit mantissa, 4x tighter than bf16; NeRF activations are far
-    inside its range).  Training: bf16 for activations AND gradients (no loss scaling needed)."""
+    """Tensor-core operand type: fp16 (10-bit mantissa, 4x tighter than bf16; NeRF activations are far inside its range)
+    for inference AND training, so that the training forward is the evaluation forward.  The 16-bit gradients of a
+    backward call are carried times one power of two chosen from the largest incoming gradient (`grad_scale`,
+    csrc/mlp_bwd.cu) -- exact, and it keeps them inside fp16's exponent range.  `YANERF_MLP_TRAIN_DTYPE=bf16` (or
+    `set_operand_dtype`) selects bf16 activations and gradients instead (fp32's exponent range, no scaling)."""
     if training:
-        return _FMT[os.environ.get("YANERF_MLP_TRAIN_DTYPE", "bf16").lower()]
+        return _FMT[os.environ.get("YANERF_MLP_TRAIN_DTYPE", "fp16").lower()]
     return _FMT[os.environ.get("YANERF_MLP_DTYPE", "fp16").lower()]
 
 
