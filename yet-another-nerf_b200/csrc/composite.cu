@@ -282,10 +282,15 @@ extern "C" int yn_composite_fwd(const yn_march_cfg* cfg, const float* raw_densit
   const int wpb = 8;
   const unsigned grid = (unsigned)((R + wpb - 1) / wpb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (ynb::blocked_S(p)) {
-    case 2: ynb::composite_fwd_blocked_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 4: ynb::composite_fwd_blocked_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 6: ynb::composite_fwd_blocked_kernel<6><<<grid, wpb * 32, 0, st>>>(p); break;
+  const bool in_kernel_noise = noise == nullptr && rng_state != nullptr && cfg->density_noise_std > 0.f;
+  if (!in_kernel_noise) p.rng.state = nullptr;
+  switch (ynb::blocked_S(p) * 2 + (in_kernel_noise ? 1 : 0)) {
+    case 4: ynb::composite_fwd_blocked_kernel<2, false><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 5: ynb::composite_fwd_blocked_kernel<2, true><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 8: ynb::composite_fwd_blocked_kernel<4, false><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 9: ynb::composite_fwd_blocked_kernel<4, true><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 12: ynb::composite_fwd_blocked_kernel<6, false><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 13: ynb::composite_fwd_blocked_kernel<6, true><<<grid, wpb * 32, 0, st>>>(p); break;
     default: ynb::composite_fwd_kernel<0><<<grid, wpb * 32, 0, st>>>(p);
   }
   return ynb::check_launch("yn_composite_fwd");
@@ -311,10 +316,15 @@ extern "C" int yn_composite_bwd(const yn_march_cfg* cfg, const float* raw_densit
   const int wpb = 8;
   const unsigned grid = (unsigned)((R + wpb - 1) / wpb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (ynb::blocked_S(p)) {
-    case 2: ynb::composite_bwd_blocked_kernel<2><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 4: ynb::composite_bwd_blocked_kernel<4><<<grid, wpb * 32, 0, st>>>(p); break;
-    case 6: ynb::composite_bwd_blocked_kernel<6><<<grid, wpb * 32, 0, st>>>(p); break;
+  const bool in_kernel_noise = noise == nullptr && rng_state != nullptr && cfg->density_noise_std > 0.f;
+  if (!in_kernel_noise) p.rng.state = nullptr;
+  switch (ynb::blocked_S(p) * 2 + (in_kernel_noise ? 1 : 0)) {
+    case 4: ynb::composite_bwd_blocked_kernel<2, false><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 5: ynb::composite_bwd_blocked_kernel<2, true><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 8: ynb::composite_bwd_blocked_kernel<4, false><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 9: ynb::composite_bwd_blocked_kernel<4, true><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 12: ynb::composite_bwd_blocked_kernel<6, false><<<grid, wpb * 32, 0, st>>>(p); break;
+    case 13: ynb::composite_bwd_blocked_kernel<6, true><<<grid, wpb * 32, 0, st>>>(p); break;
     default: ynb::composite_bwd_kernel<<<grid, wpb * 32, 0, st>>>(p);
   }
   return ynb::check_launch("yn_composite_bwd");

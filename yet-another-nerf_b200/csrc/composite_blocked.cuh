@@ -46,14 +46,16 @@ struct RayState {
 };
 
 // forward quantities of the lane's S samples (shared by the forward and the backward kernel)
-template <int S>
+// kRng: the density noise is drawn in the kernel (training with a device generator); a separate instantiation so that
+// the plain kernels keep their register budget
+template <int S, bool kRng>
 __device__ __forceinline__ void march_blocked(const MarchParams& p, int64_t base, int lane, float dn, RayState<S>& s) {
   const int s0 = lane * S;
   load_row<S>(p.z + base + s0, s.z);
   load_row<S>(p.sigma + base + s0, s.sr);
-  if (p.cfg.density_noise_std > 0.f && (p.noise != nullptr || p.rng.state != nullptr)) {
+  if (p.cfg.density_noise_std > 0.f && (kRng || p.noise != nullptr)) {
     float nz[S];
-    if (p.noise != nullptr) {
+    if (!kRng) {
       load_row<S>(p.noise + base + s0, nz);
     } else {  // in-kernel draws: the same (ray, sample) -> value map in the forward and the backward kernel
       NormalRow gen(p.rng, base / (32 * S));
@@ -95,7 +97,7 @@ __device__ __forceinline__ void march_blocked(const MarchParams& p, int64_t base
   s.E_last = __shfl_sync(0xffffffffu, s.E[S - 1], 31);
 }
 
-template <int S>
+template <int S, bool kRng>
 __global__ void __launch_bounds__(256) composite_fwd_blocked_kernel(const MarchParams p) {
   constexpr int C = 3;
   const int lane = threadIdx.x & 31;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256) composite_fwd_blocked_kernel(const MarchP
   float col[S * C];
   load_row<S * C>(p.rgb + (base + lane * S) * C, col);
   RayState<S> s;
-  march_blocked<S>(p, base, lane, dn, s);
+  march_blocked<S, kRng>(p, base, lane, dn, s);
   store_row<S>(p.weights + base + lane * S, s.w);
   float depth = 0.f, feat[C] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256) composite_fwd_blocked_kernel(const MarchP
   }
 }
 
-template <int S>
+template <int S, bool kRng>
 __global__ void __launch_bounds__(256) composite_bwd_blocked_kernel(const MarchParams p) {
   constexpr int C = 3;
   const int lane = threadIdx.x & 31;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(256) composite_bwd_blocked_kernel(const MarchP
   for (int k = 0; k < S; ++k) dwt[k] = 0.f;
   if (p.d_weights) load_row<S>(p.d_weights + base + lane * S, dwt);
   RayState<S> s;
-  march_blocked<S>(p, base, lane, dn, s);
+  march_blocked<S, kRng>(p, base, lane, dn, s);
   const float opacity = 1.f - s.E_last;
   const float a = blend ? opacity : 1.f;
   float g_op = dopac;

@@ -338,19 +338,25 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_kernel(const PdfParams p
 
 #include "sample_pdf_fast.cuh"
 
-template <int PS, int NPL>
-static void launch_fast(const ynb::PdfParams& p, cudaStream_t st) {
+template <int PS, int NPL, bool kRng>
+static void launch_fast_impl(const ynb::PdfParams& p, cudaStream_t st) {
   constexpr int P = 32 * PS;
   constexpr int CDFN = P <= 64 ? 64 : (P <= 128 ? 128 : 256);
   const int wpb = 8;
   const size_t smem = (size_t)wpb * (CDFN + 2 * P + p.sort_pow2) * sizeof(float);
-  auto kern = ynb::sample_pdf_merge_fast_kernel<PS, NPL>;
+  auto kern = ynb::sample_pdf_merge_fast_kernel<PS, NPL, kRng>;
   static size_t configured = 0;  // per instantiation; the size only depends on (PS, NPL)
   if (configured < smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
   kern<<<(unsigned)((p.R + wpb - 1) / wpb), wpb * 32, smem, st>>>(p);
+}
+
+template <int PS, int NPL>
+static void launch_fast(const ynb::PdfParams& p, cudaStream_t st) {
+  if (p.u == nullptr) launch_fast_impl<PS, NPL, true>(p, st);  // draws generated in the kernel
+  else launch_fast_impl<PS, NPL, false>(p, st);
 }
 
 static int launch_pdf(const float* lengths, const float* weights, const float* u, int64_t u_row_stride,

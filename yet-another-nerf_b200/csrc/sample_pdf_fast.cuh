@@ -30,7 +30,7 @@ __device__ __forceinline__ float aten_lane_partial8_ct(const float* wp, int j) {
   return part;
 }
 
-template <int PS, int NPL>
+template <int PS, int NPL, bool kRng>
 __global__ void __launch_bounds__(256) sample_pdf_merge_fast_kernel(const PdfParams p) {
   constexpr int P = 32 * PS, K = P - 2, NB = P - 1, N = 32 * NPL, OPL = PS + NPL;
   constexpr int CDFN = P <= 64 ? 64 : (P <= 128 ? 128 : 256);  // padded cdf length
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) sample_pdf_merge_fast_kernel(const PdfPar
 
   // ---- inverse-CDF samples; lane i owns draws NPL*i .. NPL*i + NPL - 1
   float ul[NPL], v[NPL];
-  if (p.u != nullptr) {
+  if (!kRng) {
     const float* ur = p.u + ray * p.u_stride + lane * NPL;
 #pragma unroll
     for (int k = 0; k < NPL / 2; ++k) {
