@@ -190,8 +190,11 @@ int yn_rng_fill(const int64_t* rng_state, int rng_site, int kind, float* out, in
  *   pred [B,n,C], image [B,height,width,C], xy [B,n,2] -> mse [B], huber [B]; deterministic reduction order.
  * Backward: d_pred [B,n,C] for incoming g_mse [B], g_huber [B] (either may be NULL).
  * ---------------------------------------------------------------------------------------------- */
-int yn_rgb_loss_fwd(const float* pred, const float* image, const float* xy, float* mse, float* huber, int64_t B,
-                    int64_t n, int C, int width, int height, void* stream);
+/* scratch: yn_rgb_loss_scratch_bytes(B) bytes of device memory, zeroed ONCE by the caller (partial sums + a per-image
+ * block counter that the kernel resets itself); it may be reused by later calls on the same stream. */
+int64_t yn_rgb_loss_scratch_bytes(int64_t B);
+int yn_rgb_loss_fwd(const float* pred, const float* image, const float* xy, float* mse, float* huber, void* scratch,
+                    int64_t B, int64_t n, int C, int width, int height, void* stream);
 int yn_rgb_loss_bwd(const float* pred, const float* image, const float* xy, const float* mse, const float* g_mse,
                     const float* g_huber, float* d_pred, int64_t B, int64_t n, int C, int width, int height,
                     void* stream);

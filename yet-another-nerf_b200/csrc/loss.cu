@@ -1,15 +1,14 @@
 // Per-image rgb losses of the training step in one launch each way: ground-truth gather at the sampled pixels
 // (`sample_grid`, yanerf/pipelines/utils.py:272-296: flat index = x + W_img * y) fused with the squared-error mean of
 // `_rgb_metrics` (pipelines/utils.py:137-158): mse_b = mean over (rays x channels) of (pred - gt)^2, shape (B,), and
-// huber_b = (sqrt(max(1 + mse_b / 0.03^2, 0) + 1e-4) - 1) * 0.03 (189-203).  One block per image, fixed-order tree
-// reduction: the result is deterministic.  The backward writes d(pred) for incoming d(mse_b), d(huber_b).
+// huber_b = (sqrt(max(1 + mse_b / 0.03^2, 0) + 1e-4) - 1) * 0.03 (189-203).  Fixed-order two-level reduction: the result
+// is deterministic.  The backward writes d(pred) for incoming d(mse_b), d(huber_b).
 #include <cuda_runtime.h>
 
 #include "mlp_common.cuh"
 
 namespace ynb {
 
-constexpr int kLossThreads = 1024;
 
 struct LossParams {
   const float* pred;   // [B, n, C]
@@ -29,12 +28,17 @@ __device__ __forceinline__ int64_t pixel_index(const LossParams& p, int64_t b, i
   return (int64_t)__fadd_rn(x, __fmul_rn((float)p.width, y));  // (x + W * y).long()
 }
 
-__global__ void __launch_bounds__(kLossThreads) rgb_loss_fwd_kernel(const LossParams p) {
-  __shared__ double s_part[kLossThreads / 32];
-  const int64_t b = blockIdx.x;
+// grid (kLossBlocks, B): block (k, b) sums its strided share of image b's rays in double precision into partial[b][k]; the
+// block that finishes LAST for image b (device counter) folds the kLossBlocks partial sums in index order: the result does
+// not depend on the order in which the blocks ran.
+constexpr int kLossBlocks = 16;
+__global__ void __launch_bounds__(256) rgb_loss_fwd_kernel(const LossParams p, double* __restrict__ partial, unsigned int* __restrict__ counter) {
+  __shared__ double s_part[8];
+  __shared__ bool s_last;
+  const int64_t b = blockIdx.y;
   const int64_t n_pix = (int64_t)p.width * p.height;
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < p.n; i += blockDim.x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = pixel_index(p, b, i);
     const float* gt = p.image + (b * n_pix + pix) * p.C;
     const float* pr = p.pred + (b * p.n + i) * p.C;
@@ -49,10 +53,20 @@ __global__ void __launch_bounds__(kLossThreads) rgb_loss_fwd_kernel(const LossPa
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;
-    for (int w = 0; w < kLossThreads / 32; ++w) tot += s_part[w];
+    for (int w = 0; w < 8; ++w) tot += s_part[w];
+    partial[b * kLossBlocks + blockIdx.x] = tot;
+    __threadfence();
+    s_last = atomicAdd(counter + b, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (int k = 0; k < (int)gridDim.x; ++k) tot += reinterpret_cast<volatile double*>(partial)[b * kLossBlocks + k];
     const float mse = (float)(tot / (double)(p.n * p.C));
     p.mse[b] = mse;
     p.huber[b] = (sqrtf(fmaxf(1.f + mse / (0.03f * 0.03f), 0.f) + 1e-4f) - 1.f) * 0.03f;
+    counter[b] = 0u;  // ready for the next launch (the scratch is caller-owned and zeroed once)
   }
 }
 
@@ -77,14 +91,18 @@ __global__ void __launch_bounds__(256) rgb_loss_bwd_kernel(const LossParams p, i
 
 }  // namespace ynb
 
-extern "C" int yn_rgb_loss_fwd(const float* pred, const float* image, const float* xy, float* mse, float* huber, int64_t B,
-                               int64_t n, int C, int width, int height, void* stream) {
+extern "C" int64_t yn_rgb_loss_scratch_bytes(int64_t B) { return B < 0 ? -1 : B * (ynb::kLossBlocks * 8 + 8); }
+
+extern "C" int yn_rgb_loss_fwd(const float* pred, const float* image, const float* xy, float* mse, float* huber, void* scratch,
+                               int64_t B, int64_t n, int C, int width, int height, void* stream) {
   if (B < 0 || n < 1 || C < 1 || width < 1 || height < 1) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_rgb_loss_fwd: bad sizes");
   if (B == 0) return YN_OK;
-  if (!pred || !image || !xy || !mse || !huber) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_rgb_loss_fwd: null pointer");
+  if (!pred || !image || !xy || !mse || !huber || !scratch) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_rgb_loss_fwd: null pointer");
   ynb::LossParams p = {};
   p.pred = pred; p.image = image; p.xy = xy; p.mse = mse; p.huber = huber; p.n = n; p.C = C; p.width = width; p.height = height;
-  ynb::rgb_loss_fwd_kernel<<<(unsigned)B, ynb::kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  double* partial = static_cast<double*>(scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(scratch) + B * ynb::kLossBlocks * 8);
+  ynb::rgb_loss_fwd_kernel<<<dim3(ynb::kLossBlocks, (unsigned)B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, partial, counter);
   return ynb::check_launch("yn_rgb_loss_fwd");
 }
 

@@ -70,7 +70,8 @@ SYMBOLS = {
     "yn_sample_pdf_merge": (c_int, [_P, _P, _P, c_int64, _P, c_int, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "yn_step_begin": (c_int, [_P, _P, _P]),
     "yn_train_rays": (c_int, [_P, c_int, _P, c_int64, c_int64, _P, _P, c_int, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
-    "yn_rgb_loss_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
+    "yn_rgb_loss_scratch_bytes": (c_int64, [c_int64]),
+    "yn_rgb_loss_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),
     "yn_rng_fill": (c_int, [_P, c_int, c_int, _P, c_int64, c_int, _P]),
     "yn_scatter_rays": (c_int, [_P, _P, _P, c_int, _P, c_int64, c_int64, c_int, c_int, _P]),
     "yn_rgb_loss_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, c_int, _P]),

@@ -424,6 +424,18 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: Opt
 # --------------------------------------------------------------------------- #
 # per-image rgb losses (ground-truth gather + squared-error mean)
 # --------------------------------------------------------------------------- #
+_LOSS_SCRATCH = {}
+
+
+def _loss_scratch(batch: int, device) -> torch.Tensor:
+    """Zeroed-once device scratch of `yn_rgb_loss_fwd` (partial sums + block counters the kernel resets itself); one
+    per (device, batch size): launches on a stream are ordered, so consecutive calls may share it."""
+    key = (str(device), batch)
+    if key not in _LOSS_SCRATCH:
+        _LOSS_SCRATCH[key] = torch.zeros(int(N.lib().yn_rgb_loss_scratch_bytes(batch)), dtype=torch.uint8, device=device)
+    return _LOSS_SCRATCH[key]
+
+
 class RgbLossFunction(torch.autograd.Function):
     """`sample_grid` + `_rgb_metrics` (pipelines/utils.py:137-158, 272-296) as one launch each way."""
 
@@ -434,8 +446,8 @@ class RgbLossFunction(torch.autograd.Function):
         pred, image, xy = N.f32c(pred), N.f32c(image), N.f32c(xy)
         mse = torch.empty(B, device=pred.device)
         huber = torch.empty(B, device=pred.device)
-        _call("yn_rgb_loss_fwd", N.ptr(pred), N.ptr(image), N.ptr(xy), N.ptr(mse), N.ptr(huber), B, n, C, Ww, Hh, STREAM,
-              device=pred.device)
+        _call("yn_rgb_loss_fwd", N.ptr(pred), N.ptr(image), N.ptr(xy), N.ptr(mse), N.ptr(huber),
+              N.ptr(_loss_scratch(B, pred.device), torch.uint8), B, n, C, Ww, Hh, STREAM, device=pred.device)
         ctx.save_for_backward(pred, image, xy, mse)
         return mse, huber
 
