@@ -126,9 +126,11 @@ class NeRFPipeline(torch.nn.Module):
     # see module docstring
     coalesce_chunks: bool = True
     max_points_per_launch: int = 64 << 20
-    # True = the reference's per-call range assertions on the pixel grid (device->host syncs).  FusedTrainer turns
-    # it off: a grid produced by this pipeline's own ray sampler is checked against the image size on the host.
-    validate_pixel_grid: bool = True
+    # The reference asserts `xys.max() < image size` on the device values (two device->host syncs per sampled tensor,
+    # pipelines/utils.py:283-284).  The pixel grid is produced by this pipeline's own ray sampler, so the same condition is
+    # checked on the HOST from the grid and image shapes (`_check_grid_fits`): no sync, and it also fires when a random
+    # training pick merely COULD fall outside the image.  True additionally keeps the reference's device-side assertions.
+    validate_pixel_grid: bool = False
     # (rank, world, process group) -> full-grid renders are ray-slab sharded over the group (see slab_bounds); None =
     # every rank renders whole images (the reference's DistributedSampler sharding)
     ray_shard: Optional[tuple] = None
@@ -222,19 +224,14 @@ class NeRFPipeline(torch.nn.Module):
         )
         xys = ray_bundle.xys
         validate = self.validate_pixel_grid
-        if not validate:
-            gh = image_height if (image_height is not None and image_width is not None) else self.render_image_height
-            gw = image_width if (image_height is not None and image_width is not None) else self.render_image_width
-            for t in (bg_image_rgb, image_rgb, depth_map):
-                if t is not None:
-                    assert gw <= t.shape[-2], "Invalid ray_sampler.image_width"
-                    assert gh <= t.shape[-3], "Invalid ray_sampler.image_height"
+        self._check_grid_fits(image_height, image_width, bg_image_rgb, image_rgb, depth_map)
         bg_color = sample_grid(bg_image_rgb, xys, validate) if bg_image_rgb is not None else None
 
         extracted = self._extract_features(kwargs)
 
         for fn in self.implicit_functions:
             fn.bind_args(**extracted)
+        deferred = self._defer_weight_checks()
         try:
             rendered: RendererOutput = self._render(
                 *ray_bundle, bg_color=bg_color, sampling_mode=sampling_mode,
@@ -243,6 +240,7 @@ class NeRFPipeline(torch.nn.Module):
         finally:
             for fn in self.implicit_functions:
                 fn.unbind_args()
+            self._restore_weight_checks(deferred)
 
         preds = self._get_view_metrics(raymarched=rendered, xys=xys, image_rgb=image_rgb, depth_map=depth_map,
                                        validate_grid=validate)
@@ -262,7 +260,39 @@ class NeRFPipeline(torch.nn.Module):
         objective = self._get_objective(preds)
         if objective is not None:
             preds["objective"] = objective
+        self._raise_deferred_weight_checks(deferred)
         return preds
+
+    # ------------------------------------------------------------------ host-side checks without mid-render syncs
+    def _check_grid_fits(self, image_height, image_width, *images) -> None:
+        custom = image_height is not None and image_width is not None
+        gh = image_height if custom else self.render_image_height
+        gw = image_width if custom else self.render_image_width
+        for t in images:
+            if t is not None:
+                assert gw <= t.shape[-2], "Invalid ray_sampler.image_width"
+                assert gh <= t.shape[-3], "Invalid ray_sampler.image_height"
+
+    def _defer_weight_checks(self):
+        """The refiner's "Negative weights provided." check reads a device flag (the reference syncs at the same place,
+        renderers/utils.py:123-124).  Inside a pipeline forward the read is moved to the END of the forward: the whole
+        render is queued first, the error still surfaces from the same call."""
+        refiners = [r for r in getattr(self.renderer, "_refiners", {}).values() if getattr(r, "check_weights", False)]
+        for r in refiners:
+            r.check_weights = False
+            r.last_flag = None
+        return refiners
+
+    @staticmethod
+    def _restore_weight_checks(refiners) -> None:
+        for r in refiners:
+            r.check_weights = True
+
+    @staticmethod
+    def _raise_deferred_weight_checks(refiners) -> None:
+        flags = [r.last_flag for r in refiners if r.last_flag is not None]
+        if flags and int(torch.stack([f.reshape(()) for f in flags]).max().item()) != 0:
+            raise ValueError("Negative weights provided.")
 
     def _extract_features(self, kwargs) -> Dict[str, Any]:
         extracted = collections.defaultdict(list)
@@ -298,6 +328,7 @@ class NeRFPipeline(torch.nn.Module):
         start, end, per = slab_bounds(n_rays, world, rank)
         B = poses.shape[0]
         validate = self.validate_pixel_grid
+        self._check_grid_fits(image_height, image_width, bg_image_rgb, image_rgb)
         n_local = end - start
         stages: List[torch.Tensor] = []
         sums: Dict[str, torch.Tensor] = {}
@@ -311,12 +342,14 @@ class NeRFPipeline(torch.nn.Module):
             extracted = self._extract_features(kwargs)
             for fn in self.implicit_functions:
                 fn.bind_args(**extracted)
+            deferred = self._defer_weight_checks()
             try:
                 out = self._render_local(*bundle, bg_color=bg_color, sampling_mode=RenderSamplingMode.FULL_GRID,
                                          implicit_functions=self.implicit_functions, evaluation_mode=evaluation_mode)
             finally:
                 for fn in self.implicit_functions:
                     fn.unbind_args()
+                self._restore_weight_checks(deferred)
             local = self._get_view_metrics(raymarched=out, xys=xys, image_rgb=image_rgb, depth_map=None, validate_grid=validate)
             sums = {k: v * float(n_local) for k, v in local.items() if k.endswith("rgb_mse")}  # per-slab mean -> sum
             while out is not None:
@@ -341,6 +374,8 @@ class NeRFPipeline(torch.nn.Module):
         objective = self._get_objective(preds)
         if objective is not None:
             preds["objective"] = objective
+        if n_local > 0:
+            self._raise_deferred_weight_checks(deferred)
         return preds
 
     def _render_local(self, origins, directions, lengths, xys, *, bg_color, sampling_mode, **kwargs) -> RendererOutput:
