@@ -45,6 +45,7 @@ class MLPSpec:
     n_harmonic_functions_dir: int = 4
     n_hidden_neurons_dir: int = 128
     color_dim: int = 3
+    latent_dim: int = 0  # width of the per-image global code appended to the xyz embedding (nerf_mlp.py:24, 86)
 
     @property
     def embed_xyz(self) -> int:  # models/utils.py:122
@@ -62,9 +63,10 @@ class MLPSpec:
         hidden = 256
         dims = []
         for li in range(self.n_layers):
-            din = hidden if li > 0 else self.embed_xyz
+            emb = self.embed_xyz + self.latent_dim  # nerf_mlp.py:85-86: embedding + global code
+            din = hidden if li > 0 else emb
             if li > 0 and li in self.input_skips:
-                din = hidden + self.embed_xyz
+                din = hidden + emb
             dims.append((din, hidden if li + 1 < self.n_layers else self.n_hidden_neurons_xyz))
         return dims
 
@@ -149,14 +151,21 @@ def harmonic_embedding(x: Tensor, n_freq: int) -> Tensor:
 # kernel family 2: the NeRF MLP
 # --------------------------------------------------------------------------- #
 def mlp_forward(
-    params: Dict[str, Tensor], spec: MLPSpec, origins: Tensor, directions: Tensor, lengths: Tensor
+    params: Dict[str, Tensor], spec: MLPSpec, origins: Tensor, directions: Tensor, lengths: Tensor,
+    global_codes: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Tensor]:
     """`NeRFMLP.forward` (`nerf_mlp.py:117-177`) on flat rays.
 
     origins/directions [R, 3], lengths [R, P] -> raw density [R, P], rgb [R, P, 3].
+    global_codes [R, latent_dim]: the ray's image code (`broadcast_global_code`, nerf_mlp.py:324-335: appended to the
+    xyz embedding of every point of the image), required iff spec.latent_dim > 0 (`_check_input`, 179-183).
     """
+    if (global_codes is None) != (spec.latent_dim == 0) or (global_codes is not None and global_codes.shape[-1] != spec.latent_dim):
+        raise ValueError("The shape of global codes is imcompible with the input dim of the network.")
     pts = origins[:, None, :] + lengths[:, :, None] * directions[:, None, :]  # models/utils.py:244
     emb = harmonic_embedding(pts, spec.n_harmonic_functions_xyz)
+    if global_codes is not None:
+        emb = torch.cat((emb, global_codes[:, None, :].expand(-1, emb.shape[1], -1)), dim=-1)
     y = emb
     for li in range(spec.n_layers):  # nerf_mlp.py:281-288
         if li in spec.input_skips:

@@ -155,6 +155,12 @@ MLP_CFGS = {
                   harmonic_functions_xyz_append_intput=True, n_hidden_neurons_xyz=64, n_harmonic_functions_dir=4,
                   harmonic_functions_dir_append_intput=True, n_hidden_neurons_dir=32, latent_dim=0, input_xyz=True,
                   input_dir=True, color_dim=3),
+    # the lego architecture with a 5-wide global code per image (nerf_mlp.py:158-170, 324-335); LAST, so that the random
+    # stream of the earlier cases is unchanged
+    "latent": dict(type="NeRFMLP", n_layers=8, input_skips=[5], n_harmonic_functions_xyz=10,
+                   harmonic_functions_xyz_append_intput=True, n_hidden_neurons_xyz=256, n_harmonic_functions_dir=4,
+                   harmonic_functions_dir_append_intput=True, n_hidden_neurons_dir=128, latent_dim=5, input_xyz=True,
+                   input_dir=True, color_dim=3, nerf_paper_v1=False),
 }
 
 
@@ -176,9 +182,13 @@ def golden_mlp():
             o = t32(r.uniform(-0.2, 0.2, size=(B, n, 1, 3)) + np.array([0, 0, -4.0]))
             d = t32(r.uniform(-0.4, 0.4, size=(B, n, 1, 3)) + np.array([0, 0, 1.0]))
             z = t32(np.sort(2 + 4 * r.uniform(size=(B, n, 1, P)), axis=-1))
-            with torch.no_grad():
-                res = model(o, d, z)
             key = f"{name}_g{int(gain)}"
+            codes = None
+            if cfg.get("latent_dim", 0) > 0:
+                codes = t32(r.standard_normal(size=(B, cfg["latent_dim"])))
+                out[key + "_codes"] = codes
+            with torch.no_grad():
+                res = model(o, d, z, global_codes=codes)
             out.update({key + "_o": o, key + "_d": d, key + "_z": z,
                         key + "_density": res["rays_densities"], key + "_rgb": res["rays_features"]})
     save("mlp", **out)

@@ -289,10 +289,65 @@ def test_mlp_unsupported_configs_fail_loudly():
     from tools.testing import LEGO_MLP
 
     with pytest.raises(NotImplementedError):
-        MODELS.build({**LEGO_MLP, "latent_dim": 2})
+        MODELS.build({**LEGO_MLP, "input_dir": False})
     with pytest.raises(NotImplementedError):
         mlp = MODELS.build({**LEGO_MLP, "n_harmonic_functions_xyz": 12}).to(DEV)
         mlp(torch.zeros(1, 2, 3, device=DEV), torch.ones(1, 2, 3, device=DEV), torch.ones(1, 2, 4, device=DEV))
+
+
+def test_mlp_latent_codes_golden_and_gradients(golden):
+    """`latent_dim > 0` (nerf_mlp.py:158-170, 324-335; the reference's tests/test_models.py and test_pipeline.py:37-64 use
+    it): a per-image global code appended to the xyz embedding.  The code is constant over an image, so it enters the
+    kernels as per-image effective biases; outputs against the reference (golden, B = 2 images with different codes),
+    gradients w.r.t. the code, the code columns of the weights and a bias against autograd through the oracle."""
+    from yanerf.pipelines.models import MODELS
+    from tools.testing import LEGO_MLP
+
+    g = golden("mlp")
+    spec = O.MLPSpec(latent_dim=5)
+    sd = syn.synth_mlp_state(spec.param_shapes(), 7, 1.0)
+    mlp = MODELS.build({**LEGO_MLP, "latent_dim": 5})
+    mlp.load_state_dict(sd)
+    mlp = mlp.to(DEV)
+    o, d, z, codes = (T(g[f"latent_g1_{k}"]) for k in ("o", "d", "z", "codes"))
+    with torch.no_grad():
+        out = mlp(o.to(DEV), d.to(DEV), z.to(DEV), global_codes=codes.to(DEV))
+    assert out["rays_features"].shape == g["latent_g1_rgb"].shape
+    e_rgb = float((out["rays_features"].cpu() - T(g["latent_g1_rgb"])).abs().max())
+    e_den = float((out["rays_densities"].cpu() - T(g["latent_g1_density"])).abs().max())
+    print(f"latent codes: rgb max abs {e_rgb:.2e}, raw density max abs {e_den:.2e}")
+    assert e_rgb <= 2e-3 and e_den <= 2e-3
+    with pytest.raises(ValueError):
+        mlp(o.to(DEV), d.to(DEV), z.to(DEV))  # a latent network needs its codes (nerf_mlp.py:163-164, 179-183)
+    with pytest.raises(ValueError):
+        mlp(o.to(DEV), d.to(DEV), z.to(DEV), global_codes=torch.zeros(2, 3, device=DEV))
+    # gradients
+    rs = np.random.RandomState(4)
+    B, n, P = z.shape[0], z.shape[1], z.shape[-1]
+    gd = T(rs.standard_normal(size=(B, n, 1, P, 1)).astype(np.float32))
+    gc = T(rs.standard_normal(size=(B, n, 1, P, 3)).astype(np.float32))
+    ps = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    c_ref = codes.clone().requires_grad_(True)
+    rows = c_ref[:, None, :].expand(-1, n, -1).reshape(-1, 5)
+    dens_ref, rgb_ref = O.mlp_forward(ps, spec, o.reshape(-1, 3), d.reshape(-1, 3), z.reshape(-1, P), rows)
+    ((dens_ref * gd.reshape(-1, P)).sum() + (rgb_ref * gc.reshape(-1, P, 3)).sum()).backward()
+    c_dev = codes.to(DEV).requires_grad_(True)
+    out = mlp(o.to(DEV), d.to(DEV), z.to(DEV), global_codes=c_dev)
+    ((out["rays_densities"] * gd.to(DEV)).sum() + (out["rays_features"] * gc.to(DEV)).sum()).backward()
+
+    def cos(a, b):
+        a, b = a.detach().cpu().double().reshape(-1), b.detach().double().reshape(-1)
+        return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30)), float(a.norm() / b.norm().clamp_min(1e-30))
+
+    got = dict(mlp.named_parameters())
+    for name, a, b in (("codes", c_dev.grad, c_ref.grad),
+                       ("layer 0 code columns", got["xyz_encoder.mlp.0.0.weight"].grad[:, 63:], ps["xyz_encoder.mlp.0.0.weight"].grad[:, 63:]),
+                       ("skip layer code columns", got["xyz_encoder.mlp.5.0.weight"].grad[:, 319:], ps["xyz_encoder.mlp.5.0.weight"].grad[:, 319:]),
+                       ("layer 0 bias", got["xyz_encoder.mlp.0.0.bias"].grad, ps["xyz_encoder.mlp.0.0.bias"].grad),
+                       ("layer 3 weight", got["xyz_encoder.mlp.3.0.weight"].grad, ps["xyz_encoder.mlp.3.0.weight"].grad)):
+        c, ratio = cos(a, b)
+        print(f"latent codes: d {name}: cos {c:.5f}, norm ratio {ratio:.4f}")
+        assert c >= 0.99 and abs(ratio - 1) <= 0.05, (name, c, ratio)
 
 
 # --------------------------------------------------------------------------- MLP backward

@@ -134,7 +134,7 @@ def test_ray_sampler_shapes_and_ranges():
 
 
 def test_model_output_shapes():
-    """Reference tests/test_models.py:19-55 (the latent_dim variant is outside the kernel family and raises)."""
+    """Reference tests/test_models.py:19-55 (the latent_dim variant: tests/test_gpu_kernels.py::test_mlp_latent_codes...)."""
     from yanerf.pipelines.models import MODELS
     from tools.testing import LEGO_MLP
 
@@ -145,6 +145,43 @@ def test_model_output_shapes():
     assert out["aux"] == {}
     with pytest.raises(ValueError):
         mlp(o, d, z, global_codes=torch.zeros(2, 1, 2, device=DEV))
+
+
+def test_pipeline_global_codes():
+    """Reference tests/test_pipeline.py:37-64 (`nerf_pipeline_cfg_with_conditional_mlp.py`): a latent_dim > 0 model, the
+    IdentityMapper feature extractor hands `global_codes` through to the implicit functions, B = 3 images, chunk_size_grid
+    30 forces the chunk loop in evaluation; training forward + backward reaches the code."""
+    from yanerf.pipelines import PIPELINES
+    from tools.testing import LEGO_MLP
+
+    B, H, W = 3, 6, 10
+    cfg = pipeline_cfg(H, W, 8, 16, 0.0, chunk=30)
+    cfg.model = {**LEGO_MLP, "latent_dim": 4}
+    cfg.feature_extractor = dict(type="IdentityMapper")
+    cfg.renderer.blend_output = True
+    cfg.ray_sampler.n_pts_per_ray_training = 16
+    cfg.ray_sampler.n_pts_per_ray_evaluation = 16
+    torch.manual_seed(0)
+    pipe = PIPELINES.build(cfg).to(DEV)
+    pipe.coalesce_chunks = False
+    poses, focal = syn.synth_camera(B, seed=2).to(DEV), torch.full((B,), 12.0, device=DEV)
+    image = syn.synth_image(B, H, W, seed=9).to(DEV)
+    codes = torch.randn(B, 4, device=DEV, requires_grad=True)
+    out = pipe(poses=poses, focal_lengths=focal, image_rgb=image, bg_image_rgb=image, evaluation_mode=EvaluationMode.TRAINING,
+               global_codes=codes)
+    assert out["objective"].shape == (B,)
+    out["objective"].mean().backward()
+    assert codes.grad is not None and torch.isfinite(codes.grad).all() and float(codes.grad.abs().sum()) > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pipe.parameters())
+    with torch.no_grad():
+        ev = pipe(poses=poses, focal_lengths=focal, image_rgb=image, evaluation_mode=EvaluationMode.EVALUATION,
+                  global_codes=codes.detach())
+        ev2 = pipe(poses=poses, focal_lengths=focal, image_rgb=image, evaluation_mode=EvaluationMode.EVALUATION,
+                   global_codes=codes.detach().flip(0))
+    assert ev["rendered_images"].shape == (B, H, W, 3) and torch.isfinite(ev["rendered_images"]).all()
+    assert not torch.equal(ev["rendered_images"], ev2["rendered_images"])  # the code conditions the render
+    with pytest.raises(ValueError, match="global codes"):
+        pipe(poses=poses, focal_lengths=focal, evaluation_mode=EvaluationMode.EVALUATION)
 
 
 def test_renderer_two_pass_same_model_runs():

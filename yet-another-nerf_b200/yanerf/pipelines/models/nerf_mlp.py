@@ -88,8 +88,6 @@ class NeRFMLP(torch.nn.Module):
         if not input_xyz and latent_dim <= 0:
             raise ValueError("The latent dimension has to be > 0 if xyz is not input!")
         unsupported = []
-        if latent_dim > 0:
-            unsupported.append("latent_dim > 0 (global_codes)")
         if not input_xyz or not input_dir:
             unsupported.append("input_xyz / input_dir = False")
         if not harmonic_functions_xyz_append_intput or not harmonic_functions_dir_append_intput:
@@ -115,7 +113,13 @@ class NeRFMLP(torch.nn.Module):
 
         embed_xyz = 3 * (2 * n_harmonic_functions_xyz + 1)
         embed_dir = 3 * (2 * n_harmonic_functions_dir + 1)
-        self.xyz_encoder = MLPWithInputSkips(n_layers, embed_xyz, n_hidden_neurons_xyz, embed_xyz, self.input_skips)
+        self._embed_xyz = embed_xyz
+        if latent_dim > 0:
+            self.logger.info(f"Model, use `global_codes`, latent_dim = {latent_dim}.")  # nerf_mlp.py:47-48
+        # the global code is appended to the xyz embedding (nerf_mlp.py:85-86, 324-335): layer 0 and every skip layer
+        # see embed_xyz + latent_dim input columns
+        self.xyz_encoder = MLPWithInputSkips(n_layers, embed_xyz + latent_dim, n_hidden_neurons_xyz, embed_xyz + latent_dim,
+                                             self.input_skips)
         self.intermediate_linear = torch.nn.Linear(n_hidden_neurons_xyz, n_hidden_neurons_xyz)
         torch.nn.init.xavier_uniform_(self.intermediate_linear.weight.data)
         self.density_layer = torch.nn.Linear(n_hidden_neurons_xyz, 1)
@@ -162,6 +166,9 @@ class NeRFMLP(torch.nn.Module):
     def use_flat_parameters(self, flat_leaf: Optional[torch.Tensor], flat_grad: Optional[torch.Tensor]) -> None:
         """The module's parameters are (already) consecutive views of `flat_leaf`'s storage: use it as the autograd
         leaf and let the backward kernels accumulate straight into `flat_grad` (no per-tensor cat / split / add)."""
+        if flat_leaf is not None and self.latent_dim > 0:
+            raise NotImplementedError("flat-buffer training (FusedTrainer) of a NeRFMLP with latent_dim > 0: the kernels see "
+                                      "per-image effective parameters (see `_effective_flat`); train it through autograd")
         if flat_leaf is not None:
             ps = self.ordered_parameters()
             ptr = flat_leaf.data_ptr()
@@ -187,6 +194,25 @@ class NeRFMLP(torch.nn.Module):
             entry[1] = key
         return entry[0]
 
+    def _effective_flat(self, code: torch.Tensor) -> torch.Tensor:
+        """Flat parameter vector of the code-free architecture the kernels implement, for ONE image's global code.
+        The code is constant over the image's points (`broadcast_global_code`, nerf_mlp.py:324-335), so in every layer
+        that reads the embedding its columns act as a bias: `W [emb | code] + b = W[:, :E] emb + (b + W[:, E:] code)`.
+        Built with differentiable torch ops on [dout x latent_dim] slices: autograd carries the kernels' gradient of the
+        effective parameters back to the code columns, the biases and the code itself."""
+        E, L, ps = self._embed_xyz, self.latent_dim, []
+        for li, seq in enumerate(self.xyz_encoder.mlp):
+            w, b = seq[0].weight, seq[0].bias
+            if li == 0 or li in self.xyz_encoder._input_skips:
+                keep = w.shape[1] - L  # [hidden | emb] then the code columns
+                assert keep == (E if li == 0 else 256 + E)
+                b = b + w[:, keep:] @ code
+                w = w[:, :keep]
+            ps += [w, b]
+        ps += [self.intermediate_linear.weight, self.intermediate_linear.bias, self.density_layer.weight, self.density_layer.bias,
+               self.color_layer[0].weight, self.color_layer[0].bias, self.color_layer[2].weight, self.color_layer[2].bias]
+        return torch.cat([p.reshape(-1) for p in ps])
+
     def invalidate_packed_weights(self) -> None:
         """Call after updating parameters behind torch's back (e.g. a fused optimizer kernel)."""
         for entry in self._plans.values():
@@ -198,9 +224,13 @@ class NeRFMLP(torch.nn.Module):
         """origins/directions `[B,*sp,3]`, lengths `[B,*sp,P]` -> rays_densities `[B,*sp,P,1]` (raw),
         rays_features `[B,*sp,P,color_dim]`, aux {}."""
         if global_codes is not None:
-            raise ValueError("The shape of global codes is imcompible with the input dim of the network.")
+            global_codes = global_codes.reshape(global_codes.shape[0], -1)  # nerf_mlp.py:160-161
+        if (global_codes is None) != (self.latent_dim == 0) or (global_codes is not None and global_codes.shape[-1] != self.latent_dim):
+            raise ValueError("The shape of global codes is imcompible with the input dim of the network.")  # nerf_mlp.py:163-164
         lead = lengths.shape[:-1]
         P = lengths.shape[-1]
+        if global_codes is not None:
+            return self._forward_with_codes(origins, directions, lengths, global_codes)
         flat = self._flat_leaf if self._flat_leaf is not None else self._flat()
         need_grad = torch.is_grad_enabled() and flat.requires_grad
         plan = self.plan_for(flat, need_grad)
@@ -212,5 +242,31 @@ class NeRFMLP(torch.nn.Module):
         return dict(
             rays_densities=density.reshape(*lead, P, 1),
             rays_features=rgb.reshape(*lead, P, self.color_dim),
+            aux={},
+        )
+
+    def _forward_with_codes(self, origins, directions, lengths, global_codes) -> dict:
+        """latent_dim > 0: one kernel chain per image with that image's effective parameters (`_effective_flat`)."""
+        lead, P = lengths.shape[:-1], lengths.shape[-1]
+        B = lead[0]
+        if global_codes.shape[0] != B:
+            raise ValueError("The shape of global codes is imcompible with the input dim of the network.")
+        o = N.f32c(origins.expand(*lead, 3)).reshape(B, -1, 3)
+        d = N.f32c(directions.expand(*lead, 3)).reshape(B, -1, 3)
+        z = N.f32c(lengths).reshape(B, -1, P)
+        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or global_codes.requires_grad)
+        fmt = self._fmt[bool(need_grad)]
+        dens, rgbs = [], []
+        for b in range(B):
+            flat = self._effective_flat(global_codes[b].to(o.dtype))
+            # a private plan per call: the packed image belongs to this image's code (and autograd keeps it until backward)
+            plan = ops.MlpPlan.create(N.MlpArch(*self._arch_fields, fmt), flat.device)
+            plan.pack(flat.detach())
+            density, rgb = ops.MlpFunction.apply(flat, o[b], d[b], z[b], plan, need_grad, None)
+            dens.append(density)
+            rgbs.append(rgb)
+        return dict(
+            rays_densities=torch.stack(dens).reshape(*lead, P, 1),
+            rays_features=torch.stack(rgbs).reshape(*lead, P, self.color_dim),
             aux={},
         )
