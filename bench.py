@@ -487,7 +487,8 @@ def bench_train(ctx: Ctx, shape, steps: int):
     return dict(
         metric=f"train rays/sec ({shape['name']}.yml step, {n_rays} rays/GPU, 64+{N_COARSE + n_fine} points/ray)",
         value=round(rays * steps / (total_ms * 1e-3), 1), unit="rays/s", steps=steps, ms_per_step=round(total_ms / steps, 3),
-        scaling="weak", dtype="bf16 operands, f32 accumulate / master weights",
+        scaling="weak", dtype=os.environ.get("YANERF_MLP_TRAIN_DTYPE", "f16") + " operands (16-bit gradients carried times one "
+                              "power of two per backward call), f32 accumulate / master weights",
         config={"workload": f"{shape['name']}.yml training step, {n_rays} rays/GPU, coarse+fine fwd/bwd + Adam, ray-sharded DDP",
                 "cuda_graph": use_graph, "parallelism": f"dp{world}",
                 "collective": "none (N=1)" if world == 1 else "one NCCL all-reduce (sum) of the flat 4.77 MB fp32 gradient per step, "
