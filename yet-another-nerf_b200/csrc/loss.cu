@@ -28,10 +28,11 @@ __device__ __forceinline__ int64_t pixel_index(const LossParams& p, int64_t b, i
   return (int64_t)__fadd_rn(x, __fmul_rn((float)p.width, y));  // (x + W * y).long()
 }
 
-// grid (kLossBlocks, B): block (k, b) sums its strided share of image b's rays in double precision into partial[b][k]; the
-// block that finishes LAST for image b (device counter) folds the kLossBlocks partial sums in index order: the result does
-// not depend on the order in which the blocks ran.
-constexpr int kLossBlocks = 16;
+// grid (nb, B): block (k, b) sums its strided share of image b's rays in double precision into partial[b][k]; the block
+// that finishes LAST for image b (device counter) folds the nb partial sums in index order: the result does not depend on
+// the order in which the blocks ran.  nb = 16 for training batches, 128 for full-image grids (a function of n alone).
+constexpr int kLossBlocks = 128;  // row length of `partial`
+__host__ __device__ inline int loss_blocks(int64_t n) { return n > 65536 ? kLossBlocks : 16; }
 __global__ void __launch_bounds__(256) rgb_loss_fwd_kernel(const LossParams p, double* __restrict__ partial, unsigned int* __restrict__ counter) {
   __shared__ double s_part[8];
   __shared__ bool s_last;
@@ -102,7 +103,7 @@ extern "C" int yn_rgb_loss_fwd(const float* pred, const float* image, const floa
   p.pred = pred; p.image = image; p.xy = xy; p.mse = mse; p.huber = huber; p.n = n; p.C = C; p.width = width; p.height = height;
   double* partial = static_cast<double*>(scratch);
   unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(scratch) + B * ynb::kLossBlocks * 8);
-  ynb::rgb_loss_fwd_kernel<<<dim3(ynb::kLossBlocks, (unsigned)B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, partial, counter);
+  ynb::rgb_loss_fwd_kernel<<<dim3(ynb::loss_blocks(n), (unsigned)B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, partial, counter);
   return ynb::check_launch("yn_rgb_loss_fwd");
 }
 

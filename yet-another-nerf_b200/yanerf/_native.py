@@ -110,8 +110,11 @@ def check(rc: int) -> None:
         raise _ERRORS.get(rc, RuntimeError)(msg)
 
 
-def stream_ptr() -> c_void_p:
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device_index: Optional[int] = None) -> c_void_p:
+    """Raw handle of torch's current stream on `device_index` (default: the current device)."""
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    return c_void_p(torch._C._cuda_getCurrentRawStream(device_index))
 
 
 def ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> c_void_p:

@@ -47,10 +47,11 @@ def _call(name: str, *args, device=None) -> None:
     current device).  Callers keep every converted operand in a local variable until this returns: the launch is
     stream-ordered, so a temporary may only go back to the caching allocator after the kernel has been queued."""
     fn = getattr(N.lib(), name)
-    guard = torch.cuda.device(device) if (device is not None and device.index is not None
-                                          and device.index != torch.cuda.current_device()) else contextlib.nullcontext()
-    with guard:
-        args = tuple(N.stream_ptr() if a is STREAM else a for a in args)
+    current = torch.cuda.current_device()
+    index = current if (device is None or device.index is None) else device.index
+    stream = N.stream_ptr(index)
+    args = tuple(stream if a is STREAM else a for a in args)
+    with (contextlib.nullcontext() if index == current else torch.cuda.device(index)):
         if Profiler.enabled:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()

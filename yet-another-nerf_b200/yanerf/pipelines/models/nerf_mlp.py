@@ -142,17 +142,29 @@ class NeRFMLP(torch.nn.Module):
         self._plans = {}  # fmt -> [MlpPlan, packed key]
         self._flat_leaf: Optional[torch.Tensor] = None  # set by FusedTrainer: parameters live in one flat buffer
         self._flat_grad: Optional[torch.Tensor] = None
+        self._ordered: Optional[List[torch.nn.Parameter]] = None  # cache of ordered_parameters()
+        self._flat_nograd = [None, None]  # [parameter key, flat copy] reused by no-grad forwards until a parameter changes
 
     # ------------------------------------------------------------------ parameter plumbing
     def ordered_parameters(self) -> List[torch.nn.Parameter]:
         """State-dict order = the flat layout `yn_mlp_pack_weights` expects."""
-        ps: List[torch.nn.Parameter] = []
-        for seq in self.xyz_encoder.mlp:
-            ps += [seq[0].weight, seq[0].bias]
-        ps += [self.intermediate_linear.weight, self.intermediate_linear.bias]
-        ps += [self.density_layer.weight, self.density_layer.bias]
-        ps += [self.color_layer[0].weight, self.color_layer[0].bias, self.color_layer[2].weight, self.color_layer[2].bias]
-        return ps
+        if self._ordered is None:
+            ps: List[torch.nn.Parameter] = []
+            for seq in self.xyz_encoder.mlp:
+                ps += [seq[0].weight, seq[0].bias]
+            ps += [self.intermediate_linear.weight, self.intermediate_linear.bias]
+            ps += [self.density_layer.weight, self.density_layer.bias]
+            ps += [self.color_layer[0].weight, self.color_layer[0].bias, self.color_layer[2].weight, self.color_layer[2].bias]
+            self._ordered = ps
+        return self._ordered
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float() may swap the Parameter objects
+        self._ordered = None
+        self._flat_nograd = [None, None]
+        return super()._apply(fn, *args, **kwargs)
+
+    def _param_key(self, device) -> tuple:
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.ordered_parameters())
 
     def set_operand_dtype(self, name: str, training: Optional[bool] = None) -> None:
         """'bf16' or 'fp16' tensor-core operands (fp32 accumulation either way) for inference, training or
@@ -180,11 +192,11 @@ class NeRFMLP(torch.nn.Module):
         self._flat_leaf, self._flat_grad = flat_leaf, flat_grad
         self.invalidate_packed_weights()
 
-    def plan_for(self, flat: torch.Tensor, needs_grad: bool) -> ops.MlpPlan:
+    def plan_for(self, flat: torch.Tensor, needs_grad: bool, key: Optional[tuple] = None) -> ops.MlpPlan:
         """(Re)pack the tensor-core weight image when the parameters changed since the last call."""
         fmt = self._fmt[bool(needs_grad)]
-        ps = self.ordered_parameters()
-        key = (str(flat.device),) + tuple((p.data_ptr(), p._version) for p in ps)
+        if key is None:
+            key = self._param_key(flat.device)
         entry = self._plans.get(fmt)
         if entry is None or entry[0].wpack.device != flat.device:
             entry = [ops.MlpPlan.create(N.MlpArch(*self._arch_fields, fmt), flat.device), None]
@@ -217,6 +229,7 @@ class NeRFMLP(torch.nn.Module):
         """Call after updating parameters behind torch's back (e.g. a fused optimizer kernel)."""
         for entry in self._plans.values():
             entry[1] = None
+        self._flat_nograd = [None, None]
 
     # ------------------------------------------------------------------ forward
     def forward(self, origins: torch.Tensor, directions: torch.Tensor, lengths: torch.Tensor,
@@ -231,9 +244,18 @@ class NeRFMLP(torch.nn.Module):
         P = lengths.shape[-1]
         if global_codes is not None:
             return self._forward_with_codes(origins, directions, lengths, global_codes)
-        flat = self._flat_leaf if self._flat_leaf is not None else self._flat()
+        key = None
+        if self._flat_leaf is not None:
+            flat = self._flat_leaf
+        elif torch.is_grad_enabled():
+            flat = self._flat()
+        else:  # inference: one flat copy per parameter version, not one concatenation per chunk
+            key = self._param_key(lengths.device)
+            if self._flat_nograd[0] != key:
+                self._flat_nograd = [key, self._flat().detach()]
+            flat = self._flat_nograd[1]
         need_grad = torch.is_grad_enabled() and flat.requires_grad
-        plan = self.plan_for(flat, need_grad)
+        plan = self.plan_for(flat, need_grad, key)
         o = N.f32c(origins.expand(*lead, 3)).reshape(-1, 3)
         d = N.f32c(directions.expand(*lead, 3)).reshape(-1, 3)
         z = N.f32c(lengths).reshape(-1, P)

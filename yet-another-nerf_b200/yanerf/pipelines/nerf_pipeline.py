@@ -291,7 +291,10 @@ class NeRFPipeline(torch.nn.Module):
     @staticmethod
     def _raise_deferred_weight_checks(refiners) -> None:
         flags = [r.last_flag for r in refiners if r.last_flag is not None]
-        if flags and int(torch.stack([f.reshape(()) for f in flags]).max().item()) != 0:
+        if not flags:
+            return
+        worst = flags[0] if len(flags) == 1 else torch.stack([f.reshape(()) for f in flags]).max()
+        if int(worst.item()) != 0:
             raise ValueError("Negative weights provided.")
 
     def _extract_features(self, kwargs) -> Dict[str, Any]:
@@ -351,24 +354,28 @@ class NeRFPipeline(torch.nn.Module):
                     fn.unbind_args()
                 self._restore_weight_checks(deferred)
             local = self._get_view_metrics(raymarched=out, xys=xys, image_rgb=image_rgb, depth_map=None, validate_grid=validate)
-            sums = {k: v * float(n_local) for k, v in local.items() if k.endswith("rgb_mse")}  # per-slab mean -> sum
+            sums = {k: v for k, v in local.items() if k.endswith("rgb_mse")}  # per-slab means
             while out is not None:
-                stages.append(torch.cat((out.features, out.depths, out.alpha_masks), dim=-1).reshape(B, n_local, -1))
+                stages += [out.features, out.depths, out.alpha_masks]
                 out = out.prev_stage
-            channels = stages[0].shape[-1]
-        if channels is None:  # more ranks than slabs: an empty contribution of the right width
+            channels = sum(t.shape[-1] for t in stages[:3])
+            n_stages = len(stages) // 3
+            packed = torch.cat(stages, dim=-1).reshape(B, n_local, -1)  # finest stage first; one copy for all of them
+        else:  # more ranks than slabs: an empty contribution of the right width
             channels = int(self.bg_color.numel() if self.bg_color.numel() > 1 else 3) + 2
-            stages = [poses.new_zeros(B, 0, channels) for _ in range(self.num_passes)]
-        packed = torch.cat(stages, dim=-1)  # finest stage first
+            n_stages = self.num_passes
+            packed = poses.new_zeros(B, 0, channels * n_stages)
         full = gather_slabs(packed, n_rays, per, group).reshape(B, Hh, Ww, packed.shape[-1])
         preds: Dict[str, Any] = {}
         if image_rgb is not None:
-            keys = ["loss_" + "prev_stage_" * k + "rgb_mse" for k in range(len(stages))]
-            acc = torch.stack([sums.get(k, poses.new_zeros(B)) for k in keys])
-            acc = reduce_sum(acc.contiguous(), group) / float(n_rays)
-            for k, v in zip(keys, acc):
+            keys = ["loss_" + "prev_stage_" * k + "rgb_mse" for k in range(n_stages)]
+            # slab mean -> slab sum -> (all-reduce) image sum -> image mean; the hubers of all stages in one go
+            acc = torch.stack([sums[k] for k in keys]) * float(n_local) if sums else poses.new_zeros(n_stages, B)
+            acc = reduce_sum(acc, group) / float(n_rays)
+            hub = huber(acc, scaling=0.03)
+            for k, v, h in zip(keys, acc, hub):
                 preds[k] = v
-                preds[k.replace("rgb_mse", "rgb_huber")] = huber(v, scaling=0.03)
+                preds[k.replace("rgb_mse", "rgb_huber")] = h
         fine = full[..., :channels]
         preds.update(rendered_images=fine[..., :-2], rendered_depths=fine[..., -2:-1], rendered_alpha_masks=fine[..., -1:])
         objective = self._get_objective(preds)

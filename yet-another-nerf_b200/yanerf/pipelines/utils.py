@@ -126,9 +126,8 @@ def eval_depth(pred, gt, crop: int = 0, mask=None, get_best_scale: bool = True, 
 class ViewMetrics(torch.nn.Module):
     """Per-image (shape `(B,)`) rgb mse / huber (+ optional depth abs error), keys prefixed."""
 
-    # ray counts per image up to this bound take the fused gather + loss kernel (one block per image: training batches);
-    # full-image evaluation grids use the torch ops
-    fused_max_rays: int = 65536
+    # ray counts per image up to this bound take the fused gather + loss kernel (`yn_rgb_loss_fwd`); None = no bound
+    fused_max_rays: Optional[int] = None
 
     def forward(self, image_sampling_grid, images=None, images_pred=None, depths=None, depths_pred=None,
                 loss_reweight_masks=None, keys_prefix: Optional[str] = "loss_", validate_grid: bool = True):
@@ -136,7 +135,9 @@ class ViewMetrics(torch.nn.Module):
         preds = {}
         fused = (images is not None and images_pred is not None and loss_reweight_masks is None and images.is_cuda
                  and images.ndim == 4 and images.shape[-1] == images_pred.shape[-1]
-                 and image_sampling_grid.numel() // (2 * images.shape[0]) <= self.fused_max_rays)
+                 and image_sampling_grid.numel() > 0
+                 and (self.fused_max_rays is None
+                      or image_sampling_grid.numel() // (2 * images.shape[0]) <= self.fused_max_rays))
         if fused:
             # ground-truth gather + squared-error mean in one launch (and one for the backward): `yn_rgb_loss_fwd`
             from .. import ops
