@@ -643,3 +643,76 @@ def test_runner_epoch_loop_on_device_feed():
     print("epoch stats", first["objective"], "->", last["objective"], "eval psnr", stats["loss_rgb_psnr"])
     assert trainer.step_count == 120 and last["objective"] < 0.25 * first["objective"]
     assert stats["loss_rgb_psnr"] > 18.0 and "loss_prev_stage_rgb_mse" in stats
+
+
+@pytest.mark.parametrize("case", ["bgdepth", "hardbg", "mask", "custom"])
+def test_pipeline_optional_inputs_vs_reference_golden(golden, case):
+    """The pipeline's optional inputs and renderer switches against the UNMODIFIED reference
+    (tests/golden/make_golden_variants.py): per-pixel background image + depth map with blend_output, hard white
+    background, `sampling_prob_mask` training picks, custom evaluation grid / depth range.  Same weights, inputs and
+    replayed draws; rendered values within the 16-bit-operand bound of the main golden tests, losses within 2e-3,
+    gradient norms within 2 % (density head 6 %)."""
+    g = golden("pipeline_variants")
+    B, H, W, n, n_fine = 2, 16, 20, 48, 64
+    over = {"bgdepth": dict(blend_output=True), "hardbg": dict(hard_background=True, bg_color=[1.0, 1.0, 1.0])}.get(case)
+    pipe = build_pipeline(H, W, n, n_fine, 0.0, chunk=64 * 37, renderer=over).to(DEV)
+    load_synth_nets(pipe, seeds=(31, 32), gain=1.0)
+    batch = dict(poses=syn.synth_camera(B, seed=8).to(DEV), focal_lengths=torch.full((B, 1), 25.0, device=DEV),
+                 image_rgb=syn.synth_image(B, H, W, seed=9).to(DEV))
+    if case == "bgdepth":
+        batch.update(bg_image_rgb=syn.synth_image(B, H, W, seed=10).to(DEV),
+                     depth_map=(2.0 + 4.0 * syn.synth_image(B, H, W, seed=11)[..., :1]).to(DEV))
+    dr = {k: v.to(DEV) for k, v in syn.synth_draws(B, n, H * W, 64, n_fine, seed=12).items()}
+
+    def compare(tag, preds, keys_tol):
+        for k, tol in keys_tol.items():
+            ref = T(g[f"{case}_{tag}_{k}"])
+            got = preds[k].detach().cpu()
+            assert got.shape == ref.shape, (k, got.shape, ref.shape)
+            err, mean = float((got - ref).abs().max()), float((got - ref).abs().mean())
+            print(f"{case} {tag} {k}: max abs err {err:.3e}, mean {mean:.3e} (ref magnitude {float(ref.abs().max()):.3e})")
+            assert err <= tol and mean <= tol / 4, (case, tag, k, err, mean)
+
+    loss_tol = {k: 2e-3 for k in ("loss_rgb_mse", "loss_prev_stage_rgb_mse", "loss_rgb_huber", "loss_prev_stage_rgb_huber",
+                                  "objective")}
+    image_tol = dict(rendered_images=3e-3, rendered_alpha_masks=3e-3, rendered_depths=5e-2)  # depths in [2, 6]: <= 1 %
+    if case == "hardbg":
+        # the last sample absorbs what is left of the ray and shows the WHITE background: the transmittance error of the
+        # semi-transparent random-init field (see test_eval_render_vs_reference_golden) is multiplied by 1.0 instead of a
+        # dim colour.  Measured 6.3e-3 max, mean below 1e-3.
+        image_tol["rendered_images"] = 1e-2
+    if case in ("bgdepth", "hardbg", "mask"):
+        extra = dict(sampling_prob_mask=T(g["mask_prob"]).to(DEV)) if case == "mask" else {}
+        with inject_draws([dr["pix"]], [dr["u_strat"], dr["u_pdf"]], []):
+            preds = pipe(**batch, **extra, evaluation_mode=EvaluationMode.TRAINING)
+        tol = dict(loss_tol, **image_tol)
+        if case == "bgdepth":
+            tol.update(loss_depth_abs=5e-2, loss_prev_stage_depth_abs=5e-2)
+        compare("train", preds, tol)
+        if case != "mask":
+            preds["objective"].mean().backward()
+            bad = []
+            for k, fn in enumerate(pipe.implicit_functions):
+                for name, p in fn._fn.named_parameters():
+                    ref = T(g[f"{case}_grad{k}_{name}"]).double()
+                    gk = p.grad.detach().cpu().double().reshape(-1)
+                    if float(ref[2]) < 1e-12:
+                        assert float(gk.norm()) < 1e-9, name
+                        continue
+                    dev = abs(float(gk.norm()) / float(ref[2]) - 1)
+                    if dev > (0.06 if name.startswith("density_layer") else 0.02):
+                        bad.append((k, name, round(dev, 4)))
+            assert not bad, bad
+    if case in ("bgdepth", "hardbg"):
+        with torch.no_grad():
+            ev = pipe(**batch, evaluation_mode=EvaluationMode.EVALUATION)
+        tol = dict(image_tol, loss_rgb_mse=2e-3, loss_prev_stage_rgb_mse=2e-3, objective=2e-3)
+        if case == "bgdepth":
+            tol.update(loss_depth_abs=5e-2, loss_prev_stage_depth_abs=5e-2)
+        compare("eval", ev, tol)
+    if case == "custom":
+        with torch.no_grad():
+            ev = pipe(**batch, image_height=12, image_width=10, min_depth=1.5, max_depth=5.0,
+                      evaluation_mode=EvaluationMode.EVALUATION)
+        assert ev["rendered_images"].shape == (B, 12, 10, 3)
+        compare("eval", ev, dict(image_tol, loss_rgb_mse=2e-3, loss_prev_stage_rgb_mse=2e-3, objective=2e-3))

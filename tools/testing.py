@@ -16,9 +16,10 @@ LEGO_MLP = dict(type="NeRFMLP", n_layers=8, input_skips=[5], n_harmonic_function
 
 
 def pipeline_cfg(H: int, W: int, n_rays: int, n_fine: int, noise_std: float, chunk: int,
-                 min_depth: float = 2.0, max_depth: float = 6.0, mlp: dict = None) -> ConfigDict:
-    """The `pipeline:` block of configs/nerf/lego.yml (lines 45-94) with the size knobs exposed."""
-    return ConfigDict(dict(
+                 min_depth: float = 2.0, max_depth: float = 6.0, mlp: dict = None, renderer: dict = None) -> ConfigDict:
+    """The `pipeline:` block of configs/nerf/lego.yml (lines 45-94) with the size knobs exposed; `renderer` overrides
+    entries of the renderer block."""
+    cfg = ConfigDict(dict(
         type="NeRFPipeline", chunk_size_grid=chunk, num_passes=2, output_rasterized_mc=True,
         loss_weights={"loss_prev_stage_rgb_mse": 1.0, "loss_rgb_mse": 1.0},
         model=dict(mlp or LEGO_MLP),
@@ -32,6 +33,8 @@ def pipeline_cfg(H: int, W: int, n_rays: int, n_fine: int, noise_std: float, chu
                       hard_background=False, background_density_bias=1.0e-6),
         feature_extractor=[],
     ))
+    cfg["renderer"].update(renderer or {})
+    return cfg
 
 
 def build_pipeline(H, W, n_rays, n_fine, noise_std, chunk, **kw):
