@@ -131,6 +131,19 @@ def test_ray_sampler_shapes_and_ranges():
     assert tr2.xys.shape == (B, 7, 1, 2)
     with pytest.raises(ValueError):
         rs(poses, focal, EvaluationMode.TRAINING, sampling_prob_mask=masks, n_rays_per_image=[4])
+    # mask_crop `(B, 1, H, W)`: every picked pixel lies inside the mask, distinct while the mask has enough pixels (the
+    # reference's own branch for this input raises, ray_sampler.py:82-97; the behaviour here is the evident intent)
+    crop = torch.zeros(B, 1, H, W, device=DEV)
+    crop[:, :, 2:9, 3:7] = 1.0  # 28 pixels >= 11 rays
+    tr3 = rs(poses, focal, EvaluationMode.TRAINING, mask=crop)
+    x, y = tr3.xys[..., 0].reshape(B, -1), tr3.xys[..., 1].reshape(B, -1)
+    assert tr3.xys.shape == (B, 11, 1, 2)
+    assert bool(((x >= 3) & (x < 7) & (y >= 2) & (y < 9)).all())
+    flat = (y * W + x).long()
+    assert all(len(set(row.tolist())) == 11 for row in flat)
+    half = torch.nn.functional.interpolate(crop, size=[6, 5], mode="nearest")  # a mask at another resolution is resized
+    tr4 = rs(poses, focal, EvaluationMode.TRAINING, mask=half)
+    assert tr4.xys.shape == (B, 11, 1, 2)
 
 
 def test_model_output_shapes():
