@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs the instrumented library: make -C yet-another-nerf_b200/csrc clean all INSTRUMENT=1
 # Timing experiments on the training step (gradients are wrong under these flags, only the times mean something).
 #   YN_BWD_DEBUG bit mask: 1 skip dgrad, 2 skip wgrad (+ intermediate-layer product), 4 skip heads, 8 skip direction,
 #                          32 dgrad stores into an L2-resident 64-tile window, 64 wgrad reads from such a window

@@ -1,4 +1,5 @@
 #!/bin/bash
+# needs the instrumented library: make -C yet-another-nerf_b200/csrc clean all INSTRUMENT=1
 # Where do the training forward and the data-gradient kernel lose time?  (timing experiments, wrong results)
 #   YN_FWD_DEBUG: 8 no sign masks, 16 no stash stores, 4 stash into an L2-resident window
 #   YN_BWD_DEBUG: 14 = dgrad only; +128 no mask application, +256 no gradient-stash stores

@@ -1,5 +1,8 @@
+"""Forward kernel with its epilogue work / weight copies switched off (YN_FWD_DEBUG bits 1, 2): what bounds a layer.
+Needs the instrumented library: `make -C yet-another-nerf_b200/csrc clean all INSTRUMENT=1`."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo/yet-another-nerf_b200"); sys.path.insert(0, "/root/repo")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "yet-another-nerf_b200")); sys.path.insert(0, REPO)
 from yanerf.pipelines.models.nerf_mlp import NeRFMLP
 dev = torch.device("cuda")
 torch.manual_seed(0)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Debug aid: timeline of CTA 0 of mlp_fwd_kernel (YN_FWD_TRACE): per layer, when each MMA issuer / epilogue group
+"""Debug aid (needs the instrumented library: `make -C yet-another-nerf_b200/csrc clean all INSTRUMENT=1`):
+timeline of CTA 0 of mlp_fwd_kernel (YN_FWD_TRACE): per layer, when each MMA issuer / epilogue group
 waited and for how long.  Prints cycles relative to the start of the chosen tile pair."""
 import os
 import sys

@@ -14,12 +14,21 @@
 //   3. small SIMT kernels     the N=1 / N=3 heads and the per-ray direction part of LinearWithRepeat
 //                             (models/utils.py:207-211).
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "mlp_common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace ynb {
+
+// timing-experiment flags (YN_BWD_DEBUG) exist only in `make INSTRUMENT=1` builds: the product kernels carry no
+// predicates for them
+#ifdef YN_INSTRUMENT
+__device__ __forceinline__ int debug_flags(const int flags) { return flags; }
+#else
+__device__ __forceinline__ int debug_flags(const int) { return 0; }
+#endif
 
 constexpr int kBwdRing = 4;
 constexpr int kBwdThreads = 352;  // warp 0 TMA, warps 1 and 10 MMA issuers (tile 0 / 1), warps 2-9 epilogue
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
       const bool tile_real = tile < n_tiles;
-      const bool tile_live = tile_real && !(p.debug & 256);  // (bit 256, timing experiment: no gradient-stash stores)
+      const bool tile_live = tile_real && !(debug_flags(p.debug) & 256);  // (bit 256, timing experiment: no gradient-stash stores)
       const int64_t gidx = tile * kTileM + row;
       const bool valid = gidx < p.n_points;
       // rows of partner tiles beyond the end alias tile 0 of the stash for reads; their gradients are zero
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
       // this row's ReLU sign masks (32 B per layer): mask m at A.mask_offset(m)
       const uint8_t* mask_rows = p.stash + (size_t)rtile * blocks_per_tile * kBlkBytes + (size_t)row * 32;
       // (YN_BWD_DEBUG bit 32, timing experiment: every gradient-stash store lands in a 64-tile window that stays in L2)
-      uint8_t* gstash_tile = p.gstash + (size_t)((p.debug & 32) ? rtile % 64 : rtile) * blocks_per_tile * kBlkBytes;
+      uint8_t* gstash_tile = p.gstash + (size_t)((debug_flags(p.debug) & 32) ? rtile % 64 : rtile) * blocks_per_tile * kBlkBytes;
 
       if (leader) bulk_wait_read<0>();
       bwd_named_bar_sync(1 + g, 128);
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         }
         bwd_named_bar_sync(1 + g, 128);
         // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
-        if (p.debug & 128) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mk0, swz, dd, wd, g_row);  // (timing experiment: no masks)
+        if (debug_flags(p.debug) & 128) dgrad_epilogue_half<kFmt, 0>(t_row, 0, mk0, swz, dd, wd, g_row);  // (timing experiment: no masks)
         else if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 0, mk0, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 0, mk0, swz, dd, wd, g_row);
         tc_fence_before();
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_dgrad_kernel(const Bwd
         if (leader) bulk_wait_read<1>();  // the previous step's blocks-2,3 store (most recent group: this step's blocks 0,1)
         bwd_named_bar_sync(1 + g, 128);
         // step 0 arrives at the last trunk layer's output: + the rank-1 density-head term
-        if (p.debug & 128) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mk1, swz, dd, wd, g_row);
+        if (debug_flags(p.debug) & 128) dgrad_epilogue_half<kFmt, 0>(t_row, 128, mk1, swz, dd, wd, g_row);
         else if (st == 0) dgrad_epilogue_half<kFmt, 2>(t_row, 128, mk1, swz, dd, wd, g_row);
         else dgrad_epilogue_half<kFmt, 1>(t_row, 128, mk1, swz, dd, wd, g_row);
         tc_fence_before();
@@ -458,13 +467,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
       uint32_t slot = 0, phase = 0;
       for (int64_t t = split; t < n_tiles; t += n_splits) {
         // (YN_BWD_DEBUG bit 64, timing experiment: operands come from a 64-tile window that stays in L2)
-        const int64_t ts = (p.debug & 64) ? t % 64 : t;
+        const int64_t ts = (debug_flags(p.debug) & 64) ? t % 64 : t;
         const uint8_t* st = p.stash + (size_t)ts * blocks_per_tile * kBlkBytes;
         const uint8_t* gs = p.gstash + (size_t)ts * blocks_per_tile * kBlkBytes;
         const uint32_t dst = smem_base + slot * kWgStageBytes;
         const uint32_t bar = bar_full + 8 * slot;
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-        if (p.debug & 512) {  // (timing experiment: no operand copies, the MMA pipeline alone)
+        if (debug_flags(p.debug) & 512) {  // (timing experiment: no operand copies, the MMA pipeline alone)
           mbar_arrive(bar);
           if (++slot == kWgStages) { slot = 0; phase ^= 1; }
           continue;
@@ -494,8 +503,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_bwd_wgrad_kernel(const BwdP
           const uint64_t a_desc = umma_desc_mnmajor(base + k * 2048);
           const uint32_t acc = (first && k == 0) ? 0u : 1u;
           if (has_hidden) umma_f16(tmem_base, a_desc, umma_desc_mnmajor(base + 2 * kBlkBytes + k * 2048), idesc256, acc);
-          if (has_emb && !(p.debug & 1024)) umma_f16(tmem_base + 256, a_desc, umma_desc_mnmajor(base + 6 * kBlkBytes + k * 2048), idesc64, acc);
-          if (use_ones && !(p.debug & 1024)) umma_f16(tmem_base + 320, a_desc, ones_desc, idesc16, acc);  // (1024: timing experiment)
+          if (has_emb && !(debug_flags(p.debug) & 1024)) umma_f16(tmem_base + 256, a_desc, umma_desc_mnmajor(base + 6 * kBlkBytes + k * 2048), idesc64, acc);
+          if (use_ones && !(debug_flags(p.debug) & 1024)) umma_f16(tmem_base + 320, a_desc, ones_desc, idesc16, acc);  // (1024: timing experiment)
         }
         first = 0;
         umma_commit(bar_empty + 8 * slot);
@@ -616,7 +625,7 @@ __global__ void __launch_bounds__(256, 2) mlp_bwd_heads_kernel(const BwdParams p
   fetch(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
-    if (p.debug & 16) fetch(tile);  // experiment: no prefetch
+    if (debug_flags(p.debug) & 16) fetch(tile);  // experiment: no prefetch
     if (t < kTileM) {
       s_dd[t] = nx_dd;
       s_ds[t][0] = nx_ds[0]; s_ds[t][1] = nx_ds[1]; s_ds[t][2] = nx_ds[2]; s_ds[t][3] = 0.f;
@@ -906,5 +915,12 @@ extern "C" int yn_mlp_bwd(const yn_mlp_arch* arch, const float* directions, cons
   p.P = P;
   static const int debug = getenv("YN_BWD_DEBUG") ? atoi(getenv("YN_BWD_DEBUG")) : 0;
   p.debug = debug;
+#ifndef YN_INSTRUMENT
+  static bool warned = false;
+  if ((debug & ~15) && !warned) {  // (bits 1/2/4/8 skip whole launches on the host and work in every build)
+    warned = true;
+    fprintf(stderr, "yn_mlp_bwd: YN_BWD_DEBUG bits above 8 need a `make INSTRUMENT=1` build of the library; ignored\n");
+  }
+#endif
   return ynb::launch_bwd(p, static_cast<cudaStream_t>(stream));
 }

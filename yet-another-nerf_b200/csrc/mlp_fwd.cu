@@ -52,15 +52,25 @@ struct FwdParams {
   int debug;  // timing experiments only (YN_FWD_DEBUG bit mask): 1 = epilogue skips TMEM/STS work, 2 = producer skips the copies, 4 = stash into an L2-resident window
 };
 
+// The timing experiments (YN_FWD_TRACE timeline, YN_FWD_DEBUG work-skipping flags) are compiled in only with
+// -DYN_INSTRUMENT (`make INSTRUMENT=1`): in the product build their predicates and skipped blocks sat in the hot loops
+// of the issuers and the epilogue warps and cost 1.8 % of the render (interleaved A/B on one box, tools/ab_bench.sh).
+#ifdef YN_INSTRUMENT
+constexpr bool kInstrument = true;
+#else
+constexpr bool kInstrument = false;
+#endif
 constexpr int kTraceEvents = 2048;
 struct Tracer {
   long long* buf;
   int n;
   __device__ __forceinline__ void init(long long* base, int role) {
+    if (!kInstrument) return;
     buf = (base && blockIdx.x == 0) ? base + (size_t)role * 2 * kTraceEvents : nullptr;
     n = 0;
   }
   __device__ __forceinline__ void log(int tag) {
+    if (!kInstrument) return;
     if (buf && n < kTraceEvents) {
       buf[2 * n] = tag;
       buf[2 * n + 1] = clock64();
@@ -68,6 +78,7 @@ struct Tracer {
     }
   }
 };
+__device__ __forceinline__ int debug_flags(const int flags) { return kInstrument ? flags : 0; }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           for (int j = 0; j < per_half * A.nnh(l); ++j, ++s) {
             const uint32_t bytes = (j % per_half) == nkb ? kBiasBlkBytes : kBlkBytes;
             mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-            if (p.debug & 2) {
+            if (debug_flags(p.debug) & 2) {
               mbar_arrive(bar_full + 8 * slot);
             } else {
               mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         for (int hs = 0; hs < 2; ++hs) {
           const uint32_t bytes = hs == 0 ? kDensBlkBytes : kHeadBlkBytes;
           mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-          if (p.debug & 2) {
+          if (debug_flags(p.debug) & 2) {
             mbar_arrive(bar_full + 8 * slot);
           } else {
             mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
@@ -487,8 +498,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       const bool valid = gidx < p.n_points;
       const int64_t ray = valid ? gidx / p.P : 0;
       // (YN_FWD_DEBUG bit 4, timing experiment: every stash store lands in a 64-tile window that stays in L2)
-      uint8_t* stash_tile = kStash ? p.stash + (size_t)((p.debug & 4) ? tile % 64 : tile) * blocks_per_tile * kBlkBytes : nullptr;
-      const bool tile_live = tile < n_tiles && !(kStash && (p.debug & 16));  // (bit 16, timing experiment: no stash stores)
+      uint8_t* stash_tile = kStash ? p.stash + (size_t)((debug_flags(p.debug) & 4) ? tile % 64 : tile) * blocks_per_tile * kBlkBytes : nullptr;
+      const bool tile_live = tile < n_tiles && !(kStash && (debug_flags(p.debug) & 16));  // (bit 16, timing experiment: no stash stores)
 
       if (kStash) {
         if (stash_leader) bulk_wait_read<0>();
@@ -550,9 +561,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         const bool plain = !is_color;
         // ReLU sign mask of this layer and row (training only): trunk layer l -> mask l, colour hidden -> mask n_layers
         uint8_t* mask_row = nullptr;
-        if (kStash && tile_live && !(p.debug & 8))  // (bit 8, timing experiment: no sign masks)
+        if (kStash && tile_live && !(debug_flags(p.debug) & 8))  // (bit 8, timing experiment: no sign masks)
           mask_row = stash_tile + A.mask_offset(is_color ? A.n_layers : l) + (size_t)row * 32;
-        if (p.debug & 1) {
+        if (debug_flags(p.debug) & 1) {
           before_store0();
         } else if (plain) {
           epilogue_half_plain<kFmt, true>(t_row, 0, act_row, swz, mask_row, before_store0);
@@ -581,7 +592,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           hf_phase1 ^= 1;
           tc_fence_after();
           tr.log(l << 8 | 4);
-          if (p.debug & 1) {
+          if (debug_flags(p.debug) & 1) {
           } else
             epilogue_half_plain<kFmt, true>(t_row, 128, act_row, swz, mask_row, before_store1);
           tc_fence_before();
@@ -701,6 +712,11 @@ extern "C" int yn_mlp_fwd(const yn_mlp_arch* arch, const float* origins, const f
   {
     const char* dbg = getenv("YN_FWD_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
+    static bool warned = false;
+    if (!ynb::kInstrument && !warned && (p.debug || getenv("YN_FWD_TRACE"))) {
+      warned = true;
+      fprintf(stderr, "yn_mlp_fwd: YN_FWD_DEBUG / YN_FWD_TRACE need a `make INSTRUMENT=1` build of the library; ignored\n");
+    }
   }
   p.trace = nullptr;
   if (const char* path = getenv("YN_FWD_TRACE")) {  // debug aid: synchronous, one launch per file
