@@ -79,6 +79,14 @@ struct Tracer {
   }
 };
 __device__ __forceinline__ int debug_flags(const int flags) { return kInstrument ? flags : 0; }
+// YN_FWD_DEBUG bit 128 (with YN_FWD_TRACE): no event log; CTA 0 sums the cycles its issuer 0 / epilogue group 0 / producer
+// spend in each kind of barrier wait and writes the sums to the head of their trace rows (tools/fwd_waits.py)
+#define YN_TIMED(on, acc, stmt)                 \
+  do {                                          \
+    long long t0_ = (on) ? clock64() : 0;       \
+    stmt;                                       \
+    if (on) (acc) += clock64() - t0_;           \
+  } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -252,6 +260,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
       uint32_t slot = 0, phase = 0;
+      const bool acct = kInstrument && p.trace && blockIdx.x == 0 && (p.debug & 128);
+      long long a_empty = 0, a_t0 = acct ? clock64() : 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         int s = 0;
         for (int l = 0; l < L; ++l) {
@@ -259,7 +269,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           const int per_half = A.stages_per_half(l), nkb = A.nkb(l);
           for (int j = 0; j < per_half * A.nnh(l); ++j, ++s) {
             const uint32_t bytes = (j % per_half) == nkb ? kBiasBlkBytes : kBlkBytes;
-            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            YN_TIMED(acct, a_empty, mbar_wait(bar_empty + 8 * slot, phase ^ 1));
             if (debug_flags(p.debug) & 2) {
               mbar_arrive(bar_full + 8 * slot);
             } else {
@@ -282,6 +292,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           if (++slot == kRing) { slot = 0; phase ^= 1; }
         }
       }
+      if (acct) {
+        long long* o = p.trace + (size_t)3 * 2 * kTraceEvents;
+        o[0] = 0x7a11;
+        o[1] = clock64() - a_t0;
+        o[2] = a_empty;
+      }
     }
     __syncwarp();
   } else if (warp == 1 || warp == 10) {
@@ -299,7 +315,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       uint32_t ed_phase0 = 0, ed_phase1 = 0, next_phase = 0;
       const uint32_t my_next = bar_next + 8 * g;
       Tracer tr;
-      tr.init(p.trace, g);
+      const bool acct = kInstrument && p.trace && blockIdx.x == 0 && g == 0 && (p.debug & 128);
+      tr.init((kInstrument && (p.debug & 128)) ? nullptr : p.trace, g);
+      long long a_epi0 = 0, a_epi1 = 0, a_full = 0, a_t0 = acct ? clock64() : 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int l = 0; l < L; ++l) {
           if (A.merged(l)) continue;
@@ -312,10 +330,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           if (l == 0 && pair != (int64_t)blockIdx.x) {
             // later pairs: "embedding ready, accumulator half 0 drained" comes from the previous pair's colour layer on
             // its own barrier (a second completion of epi_done[0] right behind the head's could alias its phase)
-            mbar_wait(my_next, next_phase);
+            YN_TIMED(acct, a_epi0, mbar_wait(my_next, next_phase));
             next_phase ^= 1;
           } else {
-            mbar_wait(my_epi, ed_phase0);
+            YN_TIMED(acct, a_epi0, mbar_wait(my_epi, ed_phase0));
             ed_phase0 ^= 1;
           }
           tc_fence_after();
@@ -326,13 +344,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
             for (int kb = 0; kb < nkb; ++kb) {
               if (!waited1 && (nh == 1 || (kb >= 2 && kb < nkbh))) {
                 tr.log(l << 8 | 2);
-                mbar_wait(my_epi + 8, ed_phase1);
+                YN_TIMED(acct, a_epi1, mbar_wait(my_epi + 8, ed_phase1));
                 ed_phase1 ^= 1;
                 tc_fence_after();
                 waited1 = true;
                 tr.log(l << 8 | 3);
               }
-              mbar_wait(bar_full + 8 * slot, phase);
+              YN_TIMED(acct, a_full, mbar_wait(bar_full + 8 * slot, phase));
               tc_fence_after();
               tr.log(l << 8 | 16 | (nh << 3) | kb);
               const uint64_t b_desc = umma_desc_kmajor(s_ring + slot * kBlkBytes);
@@ -414,6 +432,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           tr.log(L << 8 | 5);
         }
       }
+      if (acct) {
+        long long* o = p.trace;
+        o[0] = 0x7a11;
+        o[1] = clock64() - a_t0;
+        o[2] = a_epi0;
+        o[3] = a_epi1;
+        o[4] = a_full;
+      }
     }
     __syncwarp();
   } else if (warp >= 2 && warp <= 9) {
@@ -432,7 +458,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
     const int blocks_per_tile = A.stash_blocks_per_tile();
     uint32_t hf_phase0 = 0, hf_phase1 = 0, b01_phase = 0, df_phase = 0;
     Tracer tr;
-    tr.init(q == 0 && lane == 0 ? p.trace : nullptr, 2 + g);
+    const bool acct = kInstrument && p.trace && blockIdx.x == 0 && g == 0 && q == 0 && lane == 0 && (p.debug & 128);
+    tr.init(q == 0 && lane == 0 && !(kInstrument && (p.debug & 128)) ? p.trace : nullptr, 2 + g);
+    long long a_hf0 = 0, a_b01 = 0, a_hf1 = 0, a_head = 0, a_t0 = acct ? clock64() : 0;
     int l_emb_last = 0;  // last layer that reads the embedding block as an operand
     for (int l = 1; l < A.n_layers; ++l)
       if (A.has_emb(l)) l_emb_last = l;
@@ -536,12 +564,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         }
         // ---- half 0: accumulator columns [0,128) -> activation blocks 0,1
         tr.log(l << 8 | 0);
-        mbar_wait(my_hfull, hf_phase0);
+        YN_TIMED(acct, a_hf0, mbar_wait(my_hfull, hf_phase0));
         hf_phase0 ^= 1;
         tr.log(l << 8 | 1);
         tc_fence_after();
         auto before_store0 = [&] {
-          mbar_wait(my_b01, b01_phase);  // this layer's MMAs no longer read blocks 0,1
+          YN_TIMED(acct, a_b01, mbar_wait(my_b01, b01_phase));  // this layer's MMAs no longer read blocks 0,1
           b01_phase ^= 1;
           tc_fence_after();
           tr.log(l << 8 | 2);
@@ -588,7 +616,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         }
         // ---- half 1: columns [128,256) -> blocks 2,3 (the colour hidden layer is 128 wide: nothing to do)
         if (!is_color) {
-          mbar_wait(my_hfull + 8, hf_phase1);
+          YN_TIMED(acct, a_hf1, mbar_wait(my_hfull + 8, hf_phase1));
           hf_phase1 ^= 1;
           tc_fence_after();
           tr.log(l << 8 | 4);
@@ -617,7 +645,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
         }
         if (is_color) {
           // density head: accumulator column 144 of the tile
-          mbar_wait(bar_dfull + 8 * g, df_phase);
+          YN_TIMED(acct, a_head, mbar_wait(bar_dfull + 8 * g, df_phase));
           df_phase ^= 1;
           tc_fence_after();
           uint32_t dv[4];
@@ -626,7 +654,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
           if (valid) p.density[gidx] = __uint_as_float(dv[0]) + __ldg(p.aux + A.aux_bd());
           // colour head: 16 accumulator columns at the start of the tile's second half (the first color_dim are real);
           // the next pair's embedding arrival (program order) covers the TMEM hand-over
-          mbar_wait(my_hfull + 8, hf_phase1);
+          YN_TIMED(acct, a_head, mbar_wait(my_hfull + 8, hf_phase1));
           hf_phase1 ^= 1;
           tc_fence_after();
           uint32_t hv[4];
@@ -655,6 +683,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdParams
       }
     }
     if (kStash && stash_leader) bulk_wait<0>();
+    if (acct) {
+      long long* o = p.trace + (size_t)2 * 2 * kTraceEvents;
+      o[0] = 0x7a11;
+      o[1] = clock64() - a_t0;
+      o[2] = a_hf0;
+      o[3] = a_b01;
+      o[4] = a_hf1;
+      o[5] = a_head;
+    }
   }
 
   tc_fence_before();
