@@ -639,13 +639,14 @@ def test_device_rng_matches_explicit_draws_bitwise():
     assert not torch.equal(u, u_next) and abs(float((u * u_next).mean()) - 0.25) < 0.01  # uncorrelated
 
 
-def test_rgb_loss_and_scatter_kernels_vs_torch():
+@pytest.mark.parametrize("H,W,n", [(30, 44, 1000), (300, 400, 100000)])  # 16-block and 128-block (full-image) grids
+def test_rgb_loss_and_scatter_kernels_vs_torch(H, W, n):
     """`yn_rgb_loss_fwd/bwd` (GT gather + per-image mse / huber) and `yn_scatter_rays` against the torch ops they replace
     (the reference's sample_grid / _rgb_metrics / scatter_rays_to_image, pipelines/utils.py)."""
     from yanerf import ops
     from yanerf.pipelines.utils import _rgb_metrics, sample_grid, scatter_rays_to_image
 
-    B, H, W, n = 3, 30, 44, 1000
+    B = 3
     g = torch.Generator().manual_seed(0)
     image = torch.rand(B, H, W, 3, generator=g).to(DEV)
     idx = torch.stack([torch.randperm(H * W, generator=g)[:n] for _ in range(B)]).to(DEV)
@@ -657,8 +658,10 @@ def test_rgb_loss_and_scatter_kernels_vs_torch():
     p2 = pred.clone().requires_grad_(True)
     mse, hub = ops.rgb_loss(p2, image, xy)
     (mse * torch.tensor([1.0, 2.0, 3.0], device=DEV)).sum().add(hub.sum() * 0.5).backward()
-    close(mse, ref["rgb_mse"].detach().cpu(), 1e-6, 0, "mse")
+    close(mse, ref["rgb_mse"].detach().cpu(), 1e-6 if n <= 65536 else 3e-6, 0, "mse")  # (torch's fp32 tree sum vs fp64 here)
     close(hub, ref["rgb_huber"].detach().cpu(), 1e-5, 1e-9, "huber")
+    mse_again, _ = ops.rgb_loss(pred, image, xy)
+    same(mse_again, mse.detach().cpu(), "rgb_loss is deterministic (fixed-order fold, self-resetting counter)")
     close(p2.grad, p1.grad.cpu(), 1e-5, 1e-10, "d_pred")
     dep, alp = torch.rand(B, n, 1, device=DEV), torch.rand(B, n, 1, device=DEV)
     outs = ops.scatter_rays([pred, dep, alp], xy, H, W)
