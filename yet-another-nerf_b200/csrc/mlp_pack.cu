@@ -176,12 +176,14 @@ __global__ void pack_aux_kernel(const Arch A, const float* __restrict__ params, 
   aux[i] = v;
 }
 
-// one block = 32 rays x 128 outputs: the 27-channel embeddings of the 32 rays are built cooperatively in shared
-// memory, then thread j keeps its weight row in registers and walks the rays (coalesced 512-byte stores)
+// one block = kRays rays x 128 outputs: the 27-channel embeddings of the rays are built cooperatively in shared
+// memory, then thread j keeps its weight row in registers and walks the rays (coalesced 512-byte stores).
+// kRays = 128 for full-image renders (the per-block weight-row loads and the set-up are amortised over 4x the rays),
+// 32 for training batches (enough blocks for every SM).
+template <int kRays>
 __global__ void __launch_bounds__(128) dirbias_kernel(const Arch A, const float* __restrict__ params,
                                                      const float* __restrict__ directions,
                                                      float* __restrict__ dirbias, int64_t R) {
-  constexpr int kRays = 32;
   __shared__ __align__(16) float s_emb[kRays][32];  // rows read back as float4 broadcasts (a scalar read per FMA was LDS-bound)
   __shared__ float s_dir[kRays][3];
   const int ed = A.embed_dir();  // <= 32 (check_arch)
@@ -258,8 +260,10 @@ extern "C" int yn_mlp_dirbias(const yn_mlp_arch* arch, const float* params, cons
   if (R == 0) return YN_OK;
   if (!params || !directions || !dirbias) return ynb::fail(YN_ERR_INVALID_ARGUMENT, "yn_mlp_dirbias: null pointer");
   const ynb::Arch A = ynb::arch_from_c(arch);
-  ynb::dirbias_kernel<<<(unsigned)((R + 31) / 32), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, params, directions,
-                                                                                         dirbias, R);
+  if (R >= 64 * 1024)
+    ynb::dirbias_kernel<128><<<(unsigned)((R + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, params, directions, dirbias, R);
+  else
+    ynb::dirbias_kernel<32><<<(unsigned)((R + 31) / 32), 128, 0, static_cast<cudaStream_t>(stream)>>>(A, params, directions, dirbias, R);
   return ynb::check_launch("yn_mlp_dirbias");
 }
 
